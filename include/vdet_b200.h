@@ -1,0 +1,217 @@
+/*
+ * vdet_b200.h -- C ABI of libvdet_b200.so: the B200 (sm_100a) implementation of vdetlib's
+ * post-CNN hot path (per-frame NMS, IoU scoring / tubelet linking, temporal smoothing).
+ *
+ * vdetlib has no FFI layer: its only compiled boundary is the CPython extension
+ * `utils.cython_nms` (reference setup.py:8-15, built from utils/nms.pyx) plus plain NumPy
+ * functions.  Each entry point below names the reference interface it stands in for; the
+ * Python adapters in vdetlib_b200/{utils,vdet}/ keep the reference's function names and
+ * call these through ctypes (see INTEGRATION.md for the binding a vdetlib maintainer adds).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - plain pointers and sizes only, no torch / numpy types;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); entry points are
+ *     asynchronous unless documented "synchronous";
+ *   - no allocation inside: outputs and scratch (`ws`, sized by the matching
+ *     *_workspace_bytes query) are supplied by the caller;
+ *   - return value: VDET_OK or a negative VDET_ERR_* ; vdet_last_error() gives the
+ *     thread-local message.  Data-dependent conditions that the reference reports as Python
+ *     exceptions (ZeroDivisionError of nms.pyx:64) are written to a caller-supplied device
+ *     `status` word (bit flags VDET_STATUS_*), read by the adapter after it synchronises.
+ *   - "segments" are frames: rows [seg_offsets[s], seg_offsets[s+1]) of the packed arrays
+ *     belong to frame s.  Boxes are (x1,y1,x2,y2), "+1" pixel convention throughout.
+ */
+#ifndef VDET_B200_H_
+#define VDET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VDET_ABI_VERSION 1
+
+#define VDET_OK                 0
+#define VDET_ERR_INVALID       (-1)   /* bad argument (adapter raises ValueError)            */
+#define VDET_ERR_CUDA          (-2)   /* CUDA runtime error (adapter raises RuntimeError)    */
+#define VDET_ERR_WORKSPACE     (-3)   /* ws_bytes too small                                  */
+#define VDET_ERR_UNSUPPORTED   (-4)   /* size outside what this build handles                */
+
+#define VDET_STATUS_ZERO_DIVISION 1u  /* a same-frame pair had union == 0 (nms.pyx:64)       */
+#define VDET_STATUS_ALL_MISSING   2u  /* a tubelet row had no valid score (tubelet_cls.py:295 IndexError) */
+
+#define VDET_DTYPE_F32 0
+#define VDET_DTYPE_F64 1
+
+#define VDET_POOL_ARGMAX_SCORE 0      /* dets_spatial_max_pooling, tubelet_cls.py:334-340    */
+#define VDET_POOL_ARGMAX_IOU   1      /* anchor_propagate, tubelet_cls.py:375-377            */
+
+#define VDET_PAD_ZERO 0
+#define VDET_PAD_EDGE 1
+
+int         vdet_abi_version(void);
+const char* vdet_last_error(void);
+/* Number of SMs of `device` (grid sizing for callers); <0 on error. */
+int         vdet_sm_count(int device);
+
+/* ---------------------------------------------------------------------------------------
+ * Per-frame greedy NMS on class-shared boxes.
+ * Replaces: utils.cython_nms.nms (utils/nms.pyx:17-68) for S=1,C=1; the per-frame
+ * suppression of vid_nms (nms.pyx:71-125); and the 30 per-class apply_vid_nms passes
+ * (vdet/video_det.py:51-61) in one launch.
+ *
+ *   boxes        [n_rows, 4] float32, row stride `box_ld` floats (4 when packed; 6 with
+ *                `boxes` pointing at column 1 of a [M,6] vid_nms array)
+ *   scores       element (row r, class c) at scores[r*score_ldr + c*score_ldc]
+ *   seg_offsets  [S+1] int32, ascending, seg_offsets[S] == number of packed rows
+ *   row_ids      optional [n_rows] int32: original row of packed row p (NULL = identity).
+ *                Boxes/scores are read at row_ids[p]; outputs report row_ids[p].
+ *   thresh       IoU threshold as the reference's Python float (double); suppression test
+ *                is (double)iou_f32 >= thresh  (nms.pyx:65)
+ *   keep_idx     [C, n_rows] int32: for class c and frame s, entries
+ *                [seg_offsets[s], seg_offsets[s]+keep_cnt[c*S+s]) are the kept rows in
+ *                descending score (ties: ascending row); the rest of the frame's slots = -1
+ *   keep_cnt     [C, S] int32
+ *   keep_mask    optional [C, n_rows] uint8 (1 = kept), indexed by PACKED row p
+ *   status       [1] uint32, OR-ed with VDET_STATUS_* (never cleared by the library)
+ * max_seg_len: an upper bound of the longest frame (chooses the kernel variant); this
+ * build supports max_seg_len <= 4096.
+ * ------------------------------------------------------------------------------------- */
+size_t vdet_nms_frames_workspace_bytes(int max_seg_len, int n_classes, int device);
+int vdet_nms_frames_f32(const float* boxes, int box_ld,
+                        const float* scores, int64_t score_ldr, int64_t score_ldc,
+                        const int32_t* seg_offsets, int n_segs, int max_seg_len,
+                        const int32_t* row_ids, int n_classes, double thresh,
+                        int32_t* keep_idx, int32_t* keep_cnt, uint8_t* keep_mask,
+                        int64_t n_rows, uint32_t* status,
+                        void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Drop-in NMS entry points (SYNCHRONOUS: they return the kept count).
+ * Replace utils.cython_nms.nms / vid_nms / track_det_nms (utils/nms.pyx:17,71,128).
+ *   dets   [n, ncol] float32 row-major with row stride `ld` floats;
+ *          nms: (x1,y1,x2,y2,score); vid_nms: (frame,x1,y1,x2,y2,score)
+ *   keep   [n] int64: kept ORIGINAL row indices in GLOBAL descending score order
+ *   returns kept count (>= 0) or VDET_ERR_*; ZeroDivision is reported via *status_host.
+ * ------------------------------------------------------------------------------------- */
+size_t vdet_nms_workspace_bytes(int64_t n, int device);
+int64_t vdet_nms_f32(const float* dets, int64_t n, int ld, double thresh,
+                     int64_t* keep, uint32_t* status_host,
+                     void* ws, size_t ws_bytes, void* stream);
+int64_t vdet_vid_nms_f32(const float* dets, int64_t n, int ld, double thresh,
+                         int64_t* keep, uint32_t* status_host,
+                         void* ws, size_t ws_bytes, void* stream);
+/* tracks [q,5] = (frame,x1,y1,x2,y2), dets [k,6]; round 1 nms.pyx:163-183, round 2 :186-187 */
+int64_t vdet_track_det_nms_f32(const float* tracks, int64_t q, int tracks_ld,
+                               const float* dets, int64_t k, int dets_ld, double thresh,
+                               int64_t* keep, uint32_t* status_host,
+                               void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * One suppression step of the greedy tubelet proposal (vdet/track.py:172-183, :238-249).
+ * Device-resident state between tracker calls:
+ *   det_info   [m,6] float32 sorted by descending score (track.py:135-137 / :200-201)
+ *   seg_offsets/row_ids : frames of det_info (row_ids ascending inside a frame), from
+ *                         vdet_segment_by_frame
+ *   keep       [m] uint8, updated in place
+ * track_boxes [q,4] float32 with track_seg[q] = frame SEGMENT index (or -1: frame has no
+ * dets).  Boxes are applied in array order; two boxes on the same frame are sequenced.
+ * ------------------------------------------------------------------------------------- */
+int vdet_track_nms_step_f32(const float* det_info, int64_t m,
+                            const int32_t* seg_offsets, const int32_t* row_ids, int n_segs,
+                            const float* track_boxes, const int32_t* track_seg, int q,
+                            double thresh, uint8_t* keep, uint32_t* status, void* stream);
+
+/* Group rows by the float32 frame column (bit-equal frames, -0.0 == +0.0), stable.
+ * SYNCHRONOUS (returns counts through host pointers).
+ *   frames       pointer to the frame value of row 0, row stride `ld` floats
+ *   row_valid    optional [n] uint8: rows with 0 are dropped
+ *   row_ids_out  [n] int32 packed row -> original row (ascending inside a frame)
+ *   seg_offsets_out [n+1] int32 (first *n_segs_host+1 entries valid)
+ *   seg_frame_out   optional [n] float32: frame value of each segment                    */
+size_t vdet_segment_workspace_bytes(int64_t n);
+int vdet_segment_by_frame(const float* frames, int ld, int64_t n, const uint8_t* row_valid,
+                          int32_t* row_ids_out, int32_t* seg_offsets_out, float* seg_frame_out,
+                          int32_t* n_segs_host, int32_t* max_seg_len_host, int64_t* n_packed_host,
+                          void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Dense IoU matrix.  Replaces utils.common.iou (utils/common.py:451-468): the f64 entry
+ * reproduces its float64 arithmetic bit for bit; the f32 entry uses the float32 pair
+ * arithmetic of nms.pyx:57-64 (the HBM-roofline kernel of BASELINE.json).
+ *   a [na,4], b [nb,4] packed; out [na, nb] row-major (out_ld = nb).  union==0 -> NaN.
+ * ------------------------------------------------------------------------------------- */
+int vdet_iou_matrix_f32(const float* a, int64_t na, const float* b, int64_t nb,
+                        float* out, void* stream);
+int vdet_iou_matrix_f64(const double* a, int64_t na, const double* b, int64_t nb,
+                        double* out, void* stream);
+/* Suppression bit matrix of ONE frame in original index space:
+ * bit j of mask[i*words + j/32] = ((double)iou_f32(i,j) >= thresh); words = ceil(n/32). */
+int vdet_iou_bitmask_f32(const float* boxes, int n, double thresh, uint32_t* mask,
+                         uint32_t* status, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Frame-to-frame link (build-defined; IoU = nms.pyx pair arithmetic,
+ * FIRST arg-max as np.argmax in tubelet_cls.py:375-376).
+ * For every packed row p of frame s < S-1: succ[p] = packed row of the best box of frame
+ * s+1 (or -1 if that frame is empty), best_iou[p] = its IoU.  Rows of the LAST frame are
+ * linked against `halo_boxes` [n_halo,4] (the first frame of the next shard, from the
+ * boundary allgather); succ is then the index INTO the halo, -1 when n_halo == 0.
+ * ------------------------------------------------------------------------------------- */
+int vdet_link_frames_f32(const float* boxes, const int32_t* seg_offsets, int n_segs,
+                         int max_seg_len, const float* halo_boxes, int n_halo,
+                         int32_t* succ, float* best_iou, int64_t n_rows, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Spatial max-pooling of detections onto tubelet boxes (vdet/tubelet_cls.py:330-347,
+ * :515-532; mode ARGMAX_IOU = anchor_propagate :375-377).  IoU in float64 exactly as
+ * utils/common.py:451-468.
+ *   tub_boxes [p,4], det_boxes [n_rows,4]: float32 or float64 (box_dtype)
+ *   tub_seg   [p] int32 frame segment of each tubelet box (-1 = frame has no dets)
+ *   det_scores: element r at det_scores[r*score_ld], float32 or float64 (score_dtype)
+ *   out_arg   [p] int32 packed det row chosen, -1 when no det has IoU > thresh (strict)
+ *   out_score [p] float64: chosen det's score, or -1e5
+ * ------------------------------------------------------------------------------------- */
+int vdet_spatial_maxpool(const void* tub_boxes, const int32_t* tub_seg, int64_t p,
+                         const void* det_boxes, int box_dtype,
+                         const void* det_scores, int64_t score_ld, int score_dtype,
+                         const int32_t* det_seg_offsets, int n_segs,
+                         double thresh, int mode,
+                         int32_t* out_arg, double* out_score, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Temporal score smoothing on [n_rows, L] score rows (one row per tubelet x class), row
+ * stride `ld` elements, optional per-row lengths (NULL = all L).  dtype F32 or F64; the
+ * proto adapters use F64 (the reference works on Python floats).
+ *   completion : do_score_completion, vdet/tubelet_cls.py:284-303 (in place).  Rows with no
+ *                valid score set VDET_STATUS_ALL_MISSING.
+ *   maxpool    : score_proto_temporal_maxpool, :386-414 (window odd, pad -1e5)
+ *   conv1d     : depthwise temporal convolution, the build-defined stand-in for
+ *                score_conv_cls :15-51 (taps [n_channels, w]; row r uses channel r % n_channels)
+ * ------------------------------------------------------------------------------------- */
+int vdet_score_completion(void* scores, int dtype, int64_t n_rows, int64_t L, int64_t ld,
+                          const int32_t* lengths, double miss_thr, uint32_t* status, void* stream);
+int vdet_temporal_maxpool(const void* scores, void* out, int dtype, int64_t n_rows, int64_t L,
+                          int64_t ld, const int32_t* lengths, int window, double pad, void* stream);
+int vdet_temporal_conv1d(const void* x, void* out, int dtype, int64_t n_rows, int64_t L,
+                         int64_t ld, const int32_t* lengths, const void* taps, int n_channels,
+                         int window, int pad_mode, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Post-CNN per-class score floor + cap (vdet/video_det.py:88-100), all frames x classes.
+ *   scores [n_rows, n_classes] float32 (class 0 = background, skipped)
+ *   idx_out [S, n_classes, k] int32 local row index within the frame, -1 padded: ascending
+ *           row order when count <= k, else the top k in descending score
+ *   cnt_out [S, n_classes] int32 = min(count, k)
+ * ------------------------------------------------------------------------------------- */
+int vdet_threshold_topk_f32(const float* scores, const int32_t* seg_offsets, int n_segs,
+                            int max_seg_len, int n_classes, float thresh, int k,
+                            int32_t* idx_out, int32_t* cnt_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* VDET_B200_H_ */

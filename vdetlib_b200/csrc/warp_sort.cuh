@@ -1,0 +1,44 @@
+// warp_sort.cuh -- register-resident warp bitonic sort of 32*NPER 64-bit keys.
+#pragma once
+#include "common.cuh"
+
+namespace vdet {
+
+// ---- warp-level bitonic sort of 32*NPER 64-bit keys, blocked layout (position = lane*NPER+r)
+template <int NPER>
+__device__ __forceinline__ void warp_bitonic_sort(uint64_t (&k)[NPER], const int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32 * NPER; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= NPER) {
+                const int lstride = stride / NPER;
+                const bool lower = (lane & lstride) == 0;
+#pragma unroll
+                for (int r = 0; r < NPER; ++r) {
+                    const int q = lane * NPER + r;
+                    const bool up = (q & size) == 0;
+                    const uint64_t other = __shfl_xor_sync(FULL, k[r], lstride);
+                    const uint64_t mn = k[r] < other ? k[r] : other;
+                    const uint64_t mx = k[r] < other ? other : k[r];
+                    k[r] = (up == lower) ? mn : mx;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < NPER; ++r) {
+                    const int r2 = r ^ stride;
+                    if (r2 > r) {
+                        const int q = lane * NPER + r;
+                        const bool up = (q & size) == 0;
+                        const uint64_t a = k[r], b = k[r2];
+                        const bool sw = up ? (a > b) : (a < b);
+                        k[r] = sw ? b : a;
+                        k[r2] = sw ? a : b;
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace vdet

@@ -1,0 +1,348 @@
+"""Tensor-level operators: torch CUDA tensors in, torch CUDA tensors out.
+
+PyTorch is used for device memory and streams only; every operator is one or a few calls
+into libvdet_b200.so (include/vdet_b200.h) on ``torch.cuda.current_stream()``.  There is no
+CPU path: CPU tensors are rejected and a missing library raises RuntimeError.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+MISSING = -1e5    # utils/protocol.py:459, vdet/tubelet_cls.py:344,402
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _need(t, name, dtype=None, ndim=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError("%s must be a CUDA tensor (vdetlib_b200 has no CPU path)" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError("%s must be %d-D" % (name, ndim))
+    return t
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    """Per-device scratch buffer, grown on demand (the C ABI never allocates)."""
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def new_status(device):
+    return torch.zeros(1, dtype=torch.int32, device=device)
+
+
+def raise_for_status(status):
+    """Translate the device status word into the reference's Python exceptions (synchronises)."""
+    s = int(status.item()) & 0xffffffff
+    if s & 0x80000000:
+        raise RuntimeError("vdetlib_b200: internal frame-length mismatch")
+    if s & _lib.STATUS_ZERO_DIVISION:
+        raise ZeroDivisionError("float division")          # utils/nms.pyx:64
+    if s & _lib.STATUS_ALL_MISSING:
+        raise IndexError("list index out of range")        # vdet/tubelet_cls.py:295
+    return s
+
+
+def seg_offsets_uniform(n_frames, n_per_frame, device):
+    return torch.arange(0, (n_frames + 1) * n_per_frame, n_per_frame, dtype=torch.int32, device=device)
+
+
+# ------------------------------------------------------------------------------------------
+# NMS
+# ------------------------------------------------------------------------------------------
+def nms_frames(boxes, scores, seg_offsets, thresh, max_seg_len, row_ids=None, want_mask=False,
+               status=None, class_major=False):
+    """Greedy NMS of every (frame, class) on class-shared boxes (utils/nms.pyx:43-66 per problem).
+
+    boxes [n,4] f32; scores [n,C] f32 (or [C,n] with class_major=True, or [n]);
+    seg_offsets [S+1] i32.  Returns (keep_idx [C,n] i32, keep_cnt [C,S] i32, keep_mask|None, status).
+    """
+    lib = _lib.load()
+    _need(boxes, "boxes", torch.float32, 2)
+    _need(scores, "scores", torch.float32)
+    _need(seg_offsets, "seg_offsets", torch.int32, 1)
+    boxes = boxes.contiguous()
+    scores = scores.contiguous()
+    n = boxes.shape[0]
+    if scores.dim() == 1:
+        C, ldr, ldc = 1, 1, 0
+    elif class_major:
+        C, ldr, ldc = scores.shape[0], 1, scores.shape[1]
+    else:
+        C, ldr, ldc = scores.shape[1], scores.shape[1], 1
+    S = seg_offsets.numel() - 1
+    dev = boxes.device
+    keep_idx = torch.empty((C, n), dtype=torch.int32, device=dev)
+    keep_cnt = torch.empty((C, S), dtype=torch.int32, device=dev)
+    keep_mask = torch.empty((C, n), dtype=torch.uint8, device=dev) if want_mask else None
+    if status is None:
+        status = new_status(dev)
+    if row_ids is not None:
+        _need(row_ids, "row_ids", torch.int32, 1)
+    rc = lib.vdet_nms_frames_f32(_ptr(boxes), 4, _ptr(scores), ldr, ldc, _ptr(seg_offsets), S,
+                                 int(max_seg_len), _ptr(row_ids), C, float(thresh),
+                                 _ptr(keep_idx), _ptr(keep_cnt), _ptr(keep_mask), n, _ptr(status),
+                                 None, 0, _stream())
+    _lib.check(rc, "nms_frames")
+    return keep_idx, keep_cnt, keep_mask, status
+
+
+def _nms_entry(fn_name, dets, ncol, thresh, tracks=None):
+    lib = _lib.load()
+    _need(dets, "dets", torch.float32, 2)
+    if dets.shape[1] < ncol:
+        raise IndexError("dets needs at least %d columns" % ncol)
+    dets = dets.contiguous()
+    n, ld = dets.shape
+    dev = dets.device
+    keep = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    ws = _workspace(lib.vdet_nms_workspace_bytes(n, dev.index or 0) + 1024, dev)
+    st = ctypes.c_uint32(0)
+    if tracks is None:
+        cnt = getattr(lib, fn_name)(_ptr(dets), n, ld, float(thresh), _ptr(keep), ctypes.byref(st),
+                                    _ptr(ws), ws.numel(), _stream())
+    else:
+        _need(tracks, "tracks", torch.float32, 2)
+        if tracks.shape[1] < 5:
+            raise IndexError("tracks needs at least 5 columns")
+        tracks = tracks.contiguous()
+        cnt = lib.vdet_track_det_nms_f32(_ptr(tracks), tracks.shape[0], tracks.shape[1], _ptr(dets), n, ld,
+                                         float(thresh), _ptr(keep), ctypes.byref(st), _ptr(ws), ws.numel(),
+                                         _stream())
+    _lib.check(cnt, fn_name)
+    if st.value & _lib.STATUS_ZERO_DIVISION:
+        raise ZeroDivisionError("float division")
+    return keep[:cnt]
+
+
+def nms(dets, thresh):
+    """utils.cython_nms.nms on a CUDA tensor [N,>=5]; returns int64 kept rows, descending score."""
+    return _nms_entry("vdet_nms_f32", dets, 5, thresh)
+
+
+def vid_nms(dets, thresh):
+    """utils.cython_nms.vid_nms on a CUDA tensor [M,>=6] = (frame,x1,y1,x2,y2,score)."""
+    return _nms_entry("vdet_vid_nms_f32", dets, 6, thresh)
+
+
+def track_det_nms(tracks, dets, thresh):
+    """utils.cython_nms.track_det_nms: tracks [Q,5], dets [K,6] CUDA tensors."""
+    return _nms_entry("vdet_track_det_nms_f32", dets, 6, thresh, tracks=tracks)
+
+
+def segment_by_frame(frames, row_valid=None):
+    """Stable grouping of rows by their float32 frame value.
+
+    frames: 1-D float32 CUDA view (any stride).  Returns (row_ids i32 [n_packed], seg_offsets
+    i32 [S+1], seg_frame f32 [S], max_seg_len).  Synchronises.
+    """
+    lib = _lib.load()
+    _need(frames, "frames", torch.float32, 1)
+    n = frames.numel()
+    dev = frames.device
+    ld = frames.stride(0) if n > 1 else 1
+    row_ids = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    seg_off = torch.empty(n + 2, dtype=torch.int32, device=dev)
+    seg_frame = torch.empty(n + 1, dtype=torch.float32, device=dev)
+    ws = _workspace(lib.vdet_segment_workspace_bytes(n) + 1024, dev)
+    n_segs, max_len, n_packed = ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int64(0)
+    if row_valid is not None:
+        _need(row_valid, "row_valid", torch.uint8, 1)
+    rc = lib.vdet_segment_by_frame(_ptr(frames), ld, n, _ptr(row_valid), _ptr(row_ids), _ptr(seg_off),
+                                   _ptr(seg_frame), ctypes.byref(n_segs), ctypes.byref(max_len),
+                                   ctypes.byref(n_packed), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "segment_by_frame")
+    S = n_segs.value
+    return row_ids[:n_packed.value], seg_off[:S + 1], seg_frame[:S], max_len.value
+
+
+def track_nms_step(det_info, seg_offsets, row_ids, track_boxes, track_seg, thresh, keep, status):
+    """One tracklet's suppression pass (vdet/track.py:172-183); updates ``keep`` in place."""
+    lib = _lib.load()
+    _need(det_info, "det_info", torch.float32, 2)
+    _need(track_boxes, "track_boxes", torch.float32, 2)
+    _need(track_seg, "track_seg", torch.int32, 1)
+    _need(keep, "keep", torch.uint8, 1)
+    rc = lib.vdet_track_nms_step_f32(_ptr(det_info), det_info.shape[0], _ptr(seg_offsets), _ptr(row_ids),
+                                     seg_offsets.numel() - 1, _ptr(track_boxes), _ptr(track_seg),
+                                     track_boxes.shape[0], float(thresh), _ptr(keep), _ptr(status), _stream())
+    _lib.check(rc, "track_nms_step")
+
+
+# ------------------------------------------------------------------------------------------
+# IoU
+# ------------------------------------------------------------------------------------------
+def iou_matrix(a, b, out=None):
+    """Dense IoU [A,B].  float64 inputs: utils/common.py:451-468 bit for bit; float32 inputs:
+    the pair arithmetic of utils/nms.pyx:57-64."""
+    lib = _lib.load()
+    _need(a, "a", None, 2)
+    _need(b, "b", a.dtype, 2)
+    a = a.contiguous()
+    b = b.contiguous()
+    if out is None:
+        out = torch.empty((a.shape[0], b.shape[0]), dtype=a.dtype, device=a.device)
+    if a.dtype == torch.float32:
+        rc = lib.vdet_iou_matrix_f32(_ptr(a), a.shape[0], _ptr(b), b.shape[0], _ptr(out), _stream())
+    elif a.dtype == torch.float64:
+        rc = lib.vdet_iou_matrix_f64(_ptr(a), a.shape[0], _ptr(b), b.shape[0], _ptr(out), _stream())
+    else:
+        raise TypeError("iou_matrix: float32 or float64 boxes")
+    _lib.check(rc, "iou_matrix")
+    return out
+
+
+def iou_bitmask(boxes, thresh, status=None):
+    lib = _lib.load()
+    _need(boxes, "boxes", torch.float32, 2)
+    boxes = boxes.contiguous()
+    n = boxes.shape[0]
+    mask = torch.zeros((n, (n + 31) // 32), dtype=torch.int32, device=boxes.device)
+    if status is None:
+        status = new_status(boxes.device)
+    _lib.check(lib.vdet_iou_bitmask_f32(_ptr(boxes), n, float(thresh), _ptr(mask), _ptr(status), _stream()),
+               "iou_bitmask")
+    return mask, status
+
+
+def link_frames(boxes, seg_offsets, max_seg_len, halo=None):
+    """Frame-to-frame link: for each box, the FIRST arg-max IoU box of the next frame.
+    Returns (succ i32 [n] packed row of the successor / halo index / -1, best_iou f32 [n])."""
+    lib = _lib.load()
+    _need(boxes, "boxes", torch.float32, 2)
+    _need(seg_offsets, "seg_offsets", torch.int32, 1)
+    boxes = boxes.contiguous()
+    n = boxes.shape[0]
+    succ = torch.empty(n, dtype=torch.int32, device=boxes.device)
+    best = torch.empty(n, dtype=torch.float32, device=boxes.device)
+    n_halo = 0
+    if halo is not None:
+        _need(halo, "halo", torch.float32, 2)
+        halo = halo.contiguous()
+        n_halo = halo.shape[0]
+    rc = lib.vdet_link_frames_f32(_ptr(boxes), _ptr(seg_offsets), seg_offsets.numel() - 1, int(max_seg_len),
+                                  _ptr(halo), n_halo, _ptr(succ), _ptr(best), n, _stream())
+    _lib.check(rc, "link_frames")
+    return succ, best
+
+
+def spatial_maxpool(tub_boxes, tub_seg, det_boxes, det_scores, det_seg_offsets, thresh=0.7,
+                    mode=_lib.POOL_ARGMAX_SCORE):
+    """vdet/tubelet_cls.py:330-347 for all tubelet boxes at once.  det_scores: 1-D (strided) view of
+    the class column.  Returns (arg i32 [P] packed det row or -1, score f64 [P])."""
+    lib = _lib.load()
+    _need(tub_boxes, "tub_boxes", None, 2)
+    _need(det_boxes, "det_boxes", tub_boxes.dtype, 2)
+    _need(det_scores, "det_scores", None, 1)
+    dt = {torch.float32: _lib.DTYPE_F32, torch.float64: _lib.DTYPE_F64}
+    if tub_boxes.dtype not in dt or det_scores.dtype not in dt:
+        raise TypeError("spatial_maxpool: float32/float64 only")
+    tub_boxes = tub_boxes.contiguous()
+    det_boxes = det_boxes.contiguous()
+    P = tub_boxes.shape[0]
+    arg = torch.empty(P, dtype=torch.int32, device=tub_boxes.device)
+    score = torch.empty(P, dtype=torch.float64, device=tub_boxes.device)
+    ld = det_scores.stride(0) if det_scores.numel() > 1 else 1
+    rc = lib.vdet_spatial_maxpool(_ptr(tub_boxes), _ptr(tub_seg), P, _ptr(det_boxes), dt[tub_boxes.dtype],
+                                  _ptr(det_scores), ld, dt[det_scores.dtype], _ptr(det_seg_offsets),
+                                  det_seg_offsets.numel() - 1, float(thresh), int(mode), _ptr(arg),
+                                  _ptr(score), _stream())
+    _lib.check(rc, "spatial_maxpool")
+    return arg, score
+
+
+# ------------------------------------------------------------------------------------------
+# temporal
+# ------------------------------------------------------------------------------------------
+def _rows(x, name):
+    _need(x, name, None, 2)
+    if x.dtype not in (torch.float32, torch.float64):
+        raise TypeError("%s: float32 or float64 rows" % name)
+    if x.stride(1) != 1:
+        raise ValueError("%s: rows must be contiguous along the frame axis" % name)
+    return _lib.DTYPE_F32 if x.dtype == torch.float32 else _lib.DTYPE_F64
+
+
+def score_completion_(scores, lengths=None, miss_thr=-10.0, status=None):
+    """do_score_completion (vdet/tubelet_cls.py:284-303) on [rows, L] score rows, IN PLACE."""
+    lib = _lib.load()
+    dt = _rows(scores, "scores")
+    if status is None:
+        status = new_status(scores.device)
+    rc = lib.vdet_score_completion(_ptr(scores), dt, scores.shape[0], scores.shape[1], scores.stride(0),
+                                   _ptr(lengths), float(miss_thr), _ptr(status), _stream())
+    _lib.check(rc, "score_completion")
+    return status
+
+
+def temporal_maxpool(scores, window, lengths=None, pad=MISSING, out=None):
+    """score_proto_temporal_maxpool (vdet/tubelet_cls.py:399-409) on [rows, L] score rows."""
+    lib = _lib.load()
+    dt = _rows(scores, "scores")
+    if window % 2 != 1:
+        raise ValueError('Window size must be odd!')
+    if out is None:
+        out = torch.empty_like(scores)
+    if out.stride(0) != scores.stride(0):
+        raise ValueError("temporal_maxpool: out must have the input's row pitch")
+    rc = lib.vdet_temporal_maxpool(_ptr(scores), _ptr(out), dt, scores.shape[0], scores.shape[1],
+                                   scores.stride(0), _ptr(lengths), int(window), float(pad), _stream())
+    _lib.check(rc, "temporal_maxpool")
+    return out
+
+
+def temporal_conv1d(x, taps, pad_mode="zero", lengths=None, out=None):
+    """Depthwise temporal convolution: row r uses taps[r % n_channels]."""
+    lib = _lib.load()
+    dt = _rows(x, "x")
+    _need(taps, "taps", x.dtype, 2)
+    taps = taps.contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    if out.stride(0) != x.stride(0):
+        raise ValueError("temporal_conv1d: out must have the input's row pitch")
+    mode = {"zero": _lib.PAD_ZERO, "edge": _lib.PAD_EDGE}[pad_mode]
+    rc = lib.vdet_temporal_conv1d(_ptr(x), _ptr(out), dt, x.shape[0], x.shape[1], x.stride(0), _ptr(lengths),
+                                  _ptr(taps), taps.shape[0], taps.shape[1], mode, _stream())
+    _lib.check(rc, "temporal_conv1d")
+    return out
+
+
+def threshold_topk(scores, seg_offsets, max_seg_len, thresh=0.05, k=100):
+    """vdet/video_det.py:88-100 for every (frame, class).  scores [n, C] f32.
+    Returns (idx i32 [S, C, k] local row or -1, cnt i32 [S, C])."""
+    lib = _lib.load()
+    _need(scores, "scores", torch.float32, 2)
+    scores = scores.contiguous()
+    S = seg_offsets.numel() - 1
+    C = scores.shape[1]
+    idx = torch.empty((S, C, k), dtype=torch.int32, device=scores.device)
+    cnt = torch.empty((S, C), dtype=torch.int32, device=scores.device)
+    rc = lib.vdet_threshold_topk_f32(_ptr(scores), _ptr(seg_offsets), S, int(max_seg_len), C, float(thresh),
+                                     int(k), _ptr(idx), _ptr(cnt), _stream())
+    _lib.check(rc, "threshold_topk")
+    return idx, cnt
+
+
+def to_device(array, dtype=None, device=None):
+    """numpy / array-like -> CUDA tensor on the current device."""
+    a = np.ascontiguousarray(array, dtype=dtype)
+    return torch.from_numpy(a).to(device or torch.device("cuda", torch.cuda.current_device()))

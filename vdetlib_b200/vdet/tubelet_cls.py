@@ -1,0 +1,285 @@
+"""Drop-in for the post-CNN part of vdetlib's ``vdet.tubelet_cls`` (reference vdet/tubelet_cls.py).
+
+Same function names, arguments, defaults, return protos, in-place behaviour and exceptions as
+the reference; the per-box NumPy ``iou`` calls and the Python while-loops are replaced by one
+batched kernel launch per call (libvdet_b200.so).  Scores and boxes cross to the GPU as
+float64 so the results are the reference's Python-float results bit for bit.
+
+Out of scope here (need Caffe + images): the CNN/SVM scoring functions, reference :53-260.
+"""
+import copy
+import logging
+from collections import defaultdict
+
+import numpy as np
+import torch
+
+from .. import _lib, ops
+from ..utils.protocol import tubelets_proto_from_tracks_proto
+from .dataset import imagenet_vdet_classes
+
+
+# --------------------------------------------------------------------------------------
+# packing helpers (host side of the proto <-> tensor boundary)
+# --------------------------------------------------------------------------------------
+def _pack_rows(rows, fill=0.0):
+    """list of 1-D float sequences -> (float64 tensor [K, Lmax] on GPU, int32 lengths [K])."""
+    K = len(rows)
+    lens = np.asarray([len(r) for r in rows], dtype=np.int32)
+    L = int(lens.max()) if K else 0
+    L_pad = max(L, 1)
+    buf = np.full((K, L_pad), fill, dtype=np.float64)
+    for i, r in enumerate(rows):
+        if len(r):
+            buf[i, :len(r)] = r
+    return torch.from_numpy(buf).cuda(), torch.from_numpy(lens).cuda(), lens
+
+
+def _pool_on_gpu(tub_boxes, tub_frames, frame_dets, overlap_thres, mode):
+    """tub_boxes: list of bbox lists; tub_frames: their frame ids; frame_dets: dict
+    frame -> (det_boxes ndarray [N,4], det_scores ndarray [N]).  Returns (arg_local, score)
+    numpy arrays; arg_local indexes the frame's det arrays, -1 = no det selected."""
+    frames = sorted(frame_dets.keys())
+    seg_of = {f: s for s, f in enumerate(frames)}
+    counts = [len(frame_dets[f][0]) for f in frames]
+    seg_off = np.zeros(len(frames) + 1, dtype=np.int64)
+    np.cumsum(counts, out=seg_off[1:])
+    if len(frames):
+        det_boxes = np.concatenate([np.asarray(frame_dets[f][0], dtype=np.float64).reshape(-1, 4) for f in frames])
+        det_scores = np.concatenate([np.asarray(frame_dets[f][1], dtype=np.float64).reshape(-1) for f in frames])
+    else:
+        det_boxes = np.zeros((0, 4)); det_scores = np.zeros((0,))
+    tb = np.asarray(tub_boxes, dtype=np.float64).reshape(-1, 4)
+    seg = np.asarray([seg_of.get(f, -1) for f in tub_frames], dtype=np.int32)
+    arg, score = ops.spatial_maxpool(
+        torch.from_numpy(tb).cuda(), torch.from_numpy(seg).cuda(),
+        torch.from_numpy(det_boxes).cuda(), torch.from_numpy(det_scores).cuda(),
+        torch.from_numpy(seg_off.astype(np.int32)).cuda(), overlap_thres, mode)
+    arg = arg.cpu().numpy().astype(np.int64)
+    score = score.cpu().numpy()
+    base = np.where(seg >= 0, seg_off[np.maximum(seg, 0)], 0)
+    arg_local = np.where(arg >= 0, arg - base, -1)
+    return arg_local, score
+
+
+# --------------------------------------------------------------------------------------
+# score completion / temporal max-pool / temporal convolution
+# --------------------------------------------------------------------------------------
+def do_score_completion(score_proto):
+    """Fill runs of ``det_score <= -10`` in every tubelet, IN PLACE.  vdet/tubelet_cls.py:284-303.
+
+    A tubelet with no valid score raises IndexError like the reference (:295)."""
+    tubelets = [t for t in score_proto['tubelets'] if len(t['boxes'])]
+    if not tubelets:
+        return
+    rows = [[b['det_score'] for b in t['boxes']] for t in tubelets]
+    dev, lens_dev, lens = _pack_rows(rows)
+    status = ops.score_completion_(dev, lens_dev)
+    ops.raise_for_status(status)
+    out = dev.cpu().numpy()
+    for t, row, n in zip(tubelets, out, lens):
+        for b, v in zip(t['boxes'], row[:n]):
+            if not (b['det_score'] > -10):
+                b['det_score'] = float(v)
+
+
+def score_proto_temporal_maxpool(score_proto, window_size):
+    """Sliding max of det_score over ``window_size`` frames.  vdet/tubelet_cls.py:386-414.
+
+    As in the reference the returned proto is a SHALLOW copy (:393): the input's tubelet boxes
+    are updated in place.  ValueError for an even window (:389-390) or a gt tubelet (:396-397)."""
+    if window_size == 1:
+        return score_proto
+    if window_size % 2 != 1:
+        raise ValueError('Window size must be odd!')
+    new_score_proto = copy.copy(score_proto)
+    new_score_proto['method'] += '_temporal_maxpool_{}'.format(window_size)
+    tubelets = new_score_proto['tubelets']
+    rows = []
+    for k, tubelet in enumerate(tubelets):
+        if tubelet['gt'] == 1:
+            # the reference has already rewritten the tubelets before this one (:395-412)
+            _maxpool_rows(tubelets[:k], rows, window_size)
+            raise ValueError('Dangerous: Score file contains gt tracks!')
+        rows.append([b['det_score'] for b in tubelet['boxes']])
+    _maxpool_rows(tubelets, rows, window_size)
+    return new_score_proto
+
+
+def _maxpool_rows(tubelets, rows, window_size):
+    if not tubelets:
+        return
+    dev, lens_dev, lens = _pack_rows(rows, fill=-1e5)
+    out = ops.temporal_maxpool(dev, window_size, lens_dev).cpu().numpy()
+    for t, row, n in zip(tubelets, out, lens):
+        for b, v in zip(t['boxes'], row[:n]):
+            b['det_score'] = float(v)
+
+
+class TemporalConvNet(object):
+    """Stand-in for the Caffe net of ``score_conv_cls`` (vdet/tubelet_cls.py:15-51).
+
+    The reference feeds per-tubelet 1-D channels to an external Caffe model whose prototxt and
+    weights are not part of vdetlib (parity unpinned).  Here the "net" is an explicit
+    depthwise temporal filter: ``taps[name]`` is an odd-length 1-D filter for channel ``name``
+    (one of det_scores / track_scores / anchors / abs_anchors / gt_overlaps), the per-channel
+    responses are summed, plus ``bias``.
+    """
+
+    def __init__(self, taps, bias=0.0, pad_mode="zero"):
+        self.taps = {k: np.asarray(v, dtype=np.float64) for k, v in taps.items()}
+        self.bias = float(bias)
+        self.pad_mode = pad_mode
+
+
+def score_conv_cls(score_proto, net):
+    """Temporal-convolution rescoring: writes ``conv_score`` per box.  vdet/tubelet_cls.py:15-51
+    with ``net`` a :class:`TemporalConvNet`."""
+    new_score_proto = copy.copy(score_proto)
+    tubelets = [t for t in new_score_proto['tubelets'] if len(t['boxes'])]
+    if not tubelets:
+        return new_score_proto
+    total = None
+    for name, taps in net.taps.items():
+        rows = []
+        for t in tubelets:
+            length = len(t['boxes'])
+            if name == 'det_scores':
+                rows.append([b['det_score'] for b in t['boxes']])
+            elif name == 'track_scores':
+                rows.append([b['track_score'] for b in t['boxes']])
+            elif name == 'anchors':
+                rows.append([b['anchor'] * 1. / length for b in t['boxes']])        # :28
+            elif name == 'abs_anchors':
+                rows.append([abs(b['anchor'] * 1. / length) for b in t['boxes']])   # :30
+            elif name == 'gt_overlaps':
+                rows.append([b['gt_overlap'] for b in t['boxes']])
+            else:
+                raise KeyError(name)
+        dev, lens_dev, lens = _pack_rows(rows)
+        y = ops.temporal_conv1d(dev, torch.from_numpy(taps.reshape(1, -1)).cuda(), net.pad_mode, lens_dev)
+        total = y if total is None else total + y
+    out = (total + net.bias).cpu().numpy()
+    for t, row in zip(tubelets, out):
+        for b, v in zip(t['boxes'], row):
+            b['conv_score'] = float(v)
+    return new_score_proto
+
+
+# --------------------------------------------------------------------------------------
+# spatial max-pooling of detections onto tubelets
+# --------------------------------------------------------------------------------------
+def _spatial_max_pooling(vid_proto, tubelets_proto, frame_dets, overlap_thres):
+    """vdet/tubelet_cls.py:324-347 / :509-532 for every frame of the video at once."""
+    tub_boxes, tub_frames, where = [], [], []
+    by_frame = defaultdict(list)
+    for i, tubelet in enumerate(tubelets_proto):
+        for j, box in enumerate(tubelet['boxes']):
+            by_frame[box['frame']].append((i, j))
+    for frame in vid_proto['frames']:
+        fid = frame['frame']
+        if fid not in frame_dets:
+            continue
+        for i, j in by_frame[fid]:
+            cur = tubelets_proto[i]['boxes'][j]
+            if cur is None:
+                continue
+            tub_boxes.append(cur['bbox'])
+            tub_frames.append(fid)
+            where.append((i, j))
+    if not where:
+        return
+    arg, score = _pool_on_gpu(tub_boxes, tub_frames, frame_dets, overlap_thres, _lib.POOL_ARGMAX_SCORE)
+    for (i, j), fid, a, s in zip(where, tub_frames, arg, score):
+        cur = tubelets_proto[i]['boxes'][j]
+        if a >= 0:
+            cur['det_score'] = float(s)
+            cur['bbox'] = frame_dets[fid][0][a].tolist()
+        else:
+            logging.debug("Tubelet %d has no overlapping dets (IOU > %s).", i, overlap_thres)
+            cur['det_score'] = float(-1e5)
+
+
+def dets_spatial_max_pooling(vid_proto, track_proto, det_proto, class_idx, overlap_thres=0.7):
+    """Spatial max-pooling of a det proto onto tubelets + score completion.
+    vdet/tubelet_cls.py:305-350."""
+    assert vid_proto['video'] == track_proto['video']
+    score_proto = {}
+    score_proto['video'] = vid_proto['video']
+    score_proto['method'] = "spatial_max_pooling_IOU_{}".format(overlap_thres)
+    tubelets_proto = tubelets_proto_from_tracks_proto(track_proto['tracks'], class_idx)
+    logging.info("Sampling dets in {} for {}...".format(vid_proto['video'], imagenet_vdet_classes[class_idx]))
+
+    frame_to_det_idx = defaultdict(list)
+    dets = det_proto['detections']
+    for i, det in enumerate(dets):
+        frame_to_det_idx[det['frame']].append(i)
+    frame_dets = {}
+    for fid, idx in frame_to_det_idx.items():
+        frame_dets[fid] = (np.asarray([dets[i]['bbox'] for i in idx]),
+                           np.asarray([dets[i]['scores'][class_idx - 1]['score'] for i in idx]))   # :329
+    _spatial_max_pooling(vid_proto, tubelets_proto, frame_dets, overlap_thres)
+    score_proto['tubelets'] = tubelets_proto
+    do_score_completion(score_proto)
+    return score_proto
+
+
+def raw_dets_spatial_max_pooling(vid_proto, track_proto, frame_to_det, class_idx, overlap_thres=0.7):
+    """Same with raw per-frame arrays ``frame_to_det[frame] = (boxes [N,4], zs [N,C])``.
+    vdet/tubelet_cls.py:493-535."""
+    assert vid_proto['video'] == track_proto['video']
+    score_proto = {}
+    score_proto['video'] = vid_proto['video']
+    score_proto['method'] = "spatial_max_pooling_IOU_{}".format(overlap_thres)
+    tubelets_proto = tubelets_proto_from_tracks_proto(track_proto['tracks'], class_idx)
+    logging.info("Sampling dets in {} for {}...".format(vid_proto['video'], imagenet_vdet_classes[class_idx]))
+    frame_dets = {}
+    for fid, (det_boxes, det_scores) in frame_to_det.items():
+        if det_boxes.size == 0:
+            continue                                                     # :513
+        frame_dets[fid] = (det_boxes, det_scores[:, class_idx - 1].ravel())   # :514
+    _spatial_max_pooling(vid_proto, tubelets_proto, frame_dets, overlap_thres)
+    score_proto['tubelets'] = tubelets_proto
+    do_score_completion(score_proto)
+    return score_proto
+
+
+def anchor_propagate(vid_proto, track_proto, det_proto, class_idx):
+    """Give every box of a tubelet the class score of the det that overlaps its anchor box most.
+    vdet/tubelet_cls.py:353-383."""
+    assert vid_proto['video'] == track_proto['video']
+    score_proto = {}
+    score_proto['video'] = vid_proto['video']
+    score_proto['method'] = "anchor_propagate"
+    tubelets_proto = tubelets_proto_from_tracks_proto(track_proto['tracks'], class_idx)
+    logging.info("Propagating anchor scores in {} for {}...".format(vid_proto['video'],
+                 imagenet_vdet_classes[class_idx]))
+    dets = det_proto['detections']
+    frame_to_det_idx = defaultdict(list)
+    for i, det in enumerate(dets):
+        frame_to_det_idx[det['frame']].append(i)
+    anchors = []
+    for tubelet in tubelets_proto:
+        anchor_box = [box for box in tubelet['boxes'] if box['anchor'] == 0]
+        assert len(anchor_box) == 1
+        anchors.append(anchor_box[0])
+    frame_dets = {}
+    for a in anchors:
+        fid = a['frame']
+        if fid in frame_dets:
+            continue
+        idx = frame_to_det_idx[fid]
+        if len(idx) == 0:
+            # the reference's iou() fails on the empty 1-D det array (common.py:455)
+            raise IndexError("too many indices for array")
+        frame_dets[fid] = (np.asarray([dets[i]['bbox'] for i in idx]),
+                           np.asarray([dets[i]['scores'][class_idx - 1]['score'] for i in idx]))
+    if anchors:
+        arg, _ = _pool_on_gpu([a['bbox'] for a in anchors], [a['frame'] for a in anchors], frame_dets,
+                              0.0, _lib.POOL_ARGMAX_IOU)
+        for tubelet, a, k in zip(tubelets_proto, anchors, arg):
+            anchor_score = frame_dets[a['frame']][1][k]
+            for box in tubelet['boxes']:
+                box['det_score'] = anchor_score
+    score_proto['tubelets'] = tubelets_proto
+    return score_proto

@@ -1,0 +1,131 @@
+"""Drop-in for the post-CNN part of vdetlib's ``vdet.video_det`` (reference vdet/video_det.py).
+
+``apply_vid_nms`` keeps the reference signature and proto-in / proto-out behaviour (:51-61).
+``VideoPostProcessor`` is the packed-tensor entry for whole videos: all 30 classes of every
+frame in one launch on class-shared boxes, plus the frame-to-frame link (the path
+BASELINE.json benchmarks); it avoids the proto-dict walk that dominates the reference's host time.
+"""
+import copy
+import logging
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..utils.cython_nms import vid_nms
+from ..utils.protocol import det_score
+
+
+def apply_vid_nms(det_proto, class_index, thres=0.3):
+    """Per-frame NMS of one class over a whole det proto.  vdet/video_det.py:51-61.
+
+    As in the reference the threshold is hard-coded to 0.3 (:57) -- ``thres`` is ignored -- and
+    the returned detections are the SAME dict objects, in global descending-score order."""
+    logging.info('Apply NMS on video: {}'.format(det_proto['video']))
+    new_det = {}
+    new_det['video'] = det_proto['video']
+    boxes = np.asarray([[det['frame'], ] + list(det['bbox']) + [det_score(det, class_index), ]
+                        for det in det_proto['detections']], dtype='float32').reshape(-1, 6)
+    keep = vid_nms(boxes, thresh=0.3)
+    new_det['detections'] = copy.copy([det_proto['detections'][i] for i in keep])
+    logging.info("{} / {} windows kept.".format(len(new_det['detections']), len(det_proto['detections'])))
+    return new_det
+
+
+def threshold_topk_frames(scores, boxes, thresh=0.05, max_per_image=100):
+    """Post-CNN per-class score floor + cap for a stack of frames (vdet/video_det.py:88-100).
+
+    scores [T, R, C] float32 (class 0 = background), boxes [T, R, 4*C] float32.
+    Returns ``all_boxes[cls][frame]`` = float32 [K,5] arrays like the reference's
+    ``fast_rcnn_det_vid`` (entries of class 0 are empty lists)."""
+    scores = np.ascontiguousarray(scores, dtype=np.float32)
+    boxes = np.asarray(boxes, dtype=np.float32)
+    T, R, C = scores.shape
+    dev_scores = torch.from_numpy(scores.reshape(T * R, C)).cuda()
+    seg = ops.seg_offsets_uniform(T, R, dev_scores.device)
+    idx, cnt = ops.threshold_topk(dev_scores, seg, R, thresh, max_per_image)
+    idx = idx.cpu().numpy()
+    cnt = cnt.cpu().numpy()
+    all_boxes = [[[] for _ in range(T)] for _ in range(C)]
+    for t in range(T):
+        for j in range(1, C):
+            sel = idx[t, j, :cnt[t, j]]
+            all_boxes[j][t] = np.hstack((boxes[t, sel, j * 4:(j + 1) * 4],
+                                         scores[t, sel, j][:, np.newaxis])).astype(np.float32, copy=False)
+    return all_boxes
+
+
+class VideoPostProcessor(object):
+    """NMS (all classes) + frame-to-frame link for one video shard of fixed shape.
+
+    Input: boxes [T, N, 4] float32 and scores [T, N, C] float32 on the HOST (any array-like;
+    copied through pinned staging buffers) or already on the device.  Output (device tensors,
+    or host arrays from :meth:`run_host`):
+
+      keep_mask [C, T*N] uint8   1 = detection survives per-frame NMS for that class
+      keep_cnt  [C, T]   int32   survivors per (class, frame)
+      keep_idx  [C, T*N] int32   surviving rows per frame in descending score, -1 padded
+      succ      [T*N]    int32   packed row of the best-IoU box in the next frame (-1: none)
+      link_iou  [T*N]    float32 that IoU
+
+    ``halo`` (boxes of the first frame of the NEXT shard, [H,4]) links the shard's last frame
+    across a shard boundary (see vdetlib_b200.dist).
+    """
+
+    def __init__(self, n_frames, n_boxes, n_classes, nms_thresh=0.3, device=None, want_idx=True):
+        self.T, self.N, self.C = int(n_frames), int(n_boxes), int(n_classes)
+        self.nms_thresh = float(nms_thresh)
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.want_idx = want_idx
+        rows = self.T * self.N
+        self.seg_offsets = ops.seg_offsets_uniform(self.T, self.N, self.device)
+        self.d_boxes = torch.empty((rows, 4), dtype=torch.float32, device=self.device)
+        self.d_scores = torch.empty((rows, self.C), dtype=torch.float32, device=self.device)
+        self.h_boxes = torch.empty((rows, 4), dtype=torch.float32).pin_memory()
+        self.h_scores = torch.empty((rows, self.C), dtype=torch.float32).pin_memory()
+        self.h_mask = torch.empty((self.C, rows), dtype=torch.uint8).pin_memory()
+        self.h_cnt = torch.empty((self.C, self.T), dtype=torch.int32).pin_memory()
+        self.h_succ = torch.empty(rows, dtype=torch.int32).pin_memory()
+        self.h_iou = torch.empty(rows, dtype=torch.float32).pin_memory()
+        self.status = ops.new_status(self.device)
+
+    # bytes crossing PCIe per run_host() call
+    @property
+    def h2d_bytes(self):
+        return self.h_boxes.numel() * 4 + self.h_scores.numel() * 4
+
+    @property
+    def d2h_bytes(self):
+        return self.h_mask.numel() + self.h_cnt.numel() * 4 + self.h_succ.numel() * 4 + self.h_iou.numel() * 4
+
+    def run_device(self, d_boxes, d_scores, halo=None):
+        """Device tensors in ([T*N,4], [T*N,C]), device tensors out; asynchronous."""
+        keep_idx, keep_cnt, keep_mask, _ = ops.nms_frames(
+            d_boxes, d_scores, self.seg_offsets, self.nms_thresh, self.N, want_mask=True, status=self.status)
+        succ, link_iou = ops.link_frames(d_boxes, self.seg_offsets, self.N, halo)
+        return {"keep_idx": keep_idx, "keep_cnt": keep_cnt, "keep_mask": keep_mask,
+                "succ": succ, "link_iou": link_iou}
+
+    def stage(self, boxes, scores):
+        """Copy host arrays into the pinned staging buffers (not part of the timed region)."""
+        self.h_boxes.copy_(torch.as_tensor(np.ascontiguousarray(boxes, dtype=np.float32)).view(-1, 4))
+        self.h_scores.copy_(torch.as_tensor(np.ascontiguousarray(scores, dtype=np.float32)).view(-1, self.C))
+
+    def run_staged(self, halo=None):
+        """H2D from the pinned buffers, kernels, D2H of the results; synchronises and returns host views."""
+        self.d_boxes.copy_(self.h_boxes, non_blocking=True)
+        self.d_scores.copy_(self.h_scores, non_blocking=True)
+        out = self.run_device(self.d_boxes, self.d_scores, halo)
+        self.h_mask.copy_(out["keep_mask"], non_blocking=True)
+        self.h_cnt.copy_(out["keep_cnt"], non_blocking=True)
+        self.h_succ.copy_(out["succ"], non_blocking=True)
+        self.h_iou.copy_(out["link_iou"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        ops.raise_for_status(self.status)
+        return {"keep_mask": self.h_mask.numpy(), "keep_cnt": self.h_cnt.numpy(),
+                "succ": self.h_succ.numpy(), "link_iou": self.h_iou.numpy()}
+
+    def run_host(self, boxes, scores, halo=None):
+        """The user-facing call: host arrays in, host arrays out."""
+        self.stage(boxes, scores)
+        return self.run_staged(halo)
