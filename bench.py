@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- boxes/sec of the post-CNN hot path (per-frame NMS of all classes + tubelet link).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload = BASELINE.json configs[1]: a 1000-frame synthetic vid proto, 300 boxes/frame, 30 VID
+classes, NMS IoU 0.3 (the reference default), per GPU (weak scaling: every rank holds its own
+1000-frame shard of one long video; the link at shard boundaries uses one all-gather of
+first-frame boxes).  A "step" = one pass of NMS(all classes) + link over the shard.
+
+One JSON line on rank 0 (see the task contract): value = whole-job boxes/s with inputs resident
+in HBM; e2e = the same through the public host-buffer API (H2D + kernels + D2H per step);
+roofline = the dominant kernel of the step against the measured HBM peak; cpu_baseline = the
+reference's Cython NMS (oracle/_ref) + the C port of the link, single thread, bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+T_FRAMES, N_BOXES, N_CLASSES, NMS_THRESH = 1000, 300, 30, 0.3
+NSETS = 4                       # rotating input sets: defeats L2 reuse between timed iterations
+METRIC = "boxes/sec (NMS+tubelet-link)"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi, started before and killed after the timed regions)
+# ------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,utilization.gpu,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.out = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "50", "-i", str(gpu_index)], stdout=self.out, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.out.flush()
+        rows = []
+        with open(self.out.name) as f:
+            for line in f:
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) >= 8:
+                    rows.append(parts)
+        os.unlink(self.out.name)
+        busy = [r for r in rows if r[3].isdigit() and int(r[3]) > 0] or rows
+        sm = [float(r[0]) for r in busy if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[4 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(rows), "samples_under_load": len(busy)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU side: the reference's own implementation of the path
+# ------------------------------------------------------------------------------------------
+_REF = {}
+
+
+def _ref_init():
+    """Per-process: the real reference Cython NMS when oracle/_ref exists, else the C port."""
+    from oracle import build_ref, c_oracle
+    mod = None
+    try:
+        mod = build_ref.load()
+    except Exception:
+        mod = None
+    _REF["nms"] = mod.nms if mod is not None else c_oracle.nms
+    _REF["kind"] = "reference" if mod is not None else "port"
+    _REF["link"] = c_oracle.link_f32
+
+
+def _ref_frames(job):
+    """NMS of every class of each frame (the per-(frame,class) loop apply_vid_nms amounts to) and
+    the link to the next frame, for a chunk of frames.  Returns the number of boxes processed."""
+    import numpy as np
+    boxes, scores = job           # [F+1, N, 4], [F, N, C]
+    F, N, C = scores.shape
+    if "nms" not in _REF:
+        _ref_init()
+    nms = _REF["nms"]
+    dets = np.empty((N, 5), np.float32)
+    for t in range(F):
+        dets[:, :4] = boxes[t]
+        for c in range(C):
+            dets[:, 4] = scores[t, :, c]
+            nms(dets, NMS_THRESH)
+    _REF["link"](boxes)           # F frame pairs (C port of the build-defined link)
+    return F * N
+
+
+def cpu_baseline(sample_frames=200):
+    """Single-thread reference path on a bounded sample (rank 0, N=1 only)."""
+    from vdetlib_b200 import synth
+    _ref_init()
+    b, s = synth.boxes_scores(sample_frames + 1, N_BOXES, N_CLASSES, seed=999)
+    _ref_frames((b[:3], s[:2]))                                   # warm
+    t0 = time.perf_counter()
+    n = _ref_frames((b, s[:sample_frames]))
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "boxes/s", "cores": 1, "kind": _REF["kind"],
+            "sample": "%d frames x %d boxes x %d classes: utils/nms.pyx nms (%s) per (frame,class) + C port of "
+                      "the link per frame pair, one thread, %.1f s" % (sample_frames, N_BOXES, N_CLASSES,
+                                                                       "compiled from the reference" if _REF["kind"] == "reference" else "C restatement", dt)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+    from vdetlib_b200 import synth
+    cores = os.cpu_count() or 1
+    per_worker = 2
+    F = cores * per_worker
+    b, s = synth.boxes_scores(F + 1, N_BOXES, N_CLASSES, seed=999)
+    jobs = [(b[i * per_worker:(i + 1) * per_worker + 1], s[i * per_worker:(i + 1) * per_worker]) for i in range(cores)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_ref_init) as pool:
+        for _ in range(max(args.warmup, 1)):
+            pool.map(_ref_frames, jobs)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            n = sum(pool.map(_ref_frames, jobs))
+        dt = time.perf_counter() - t0
+    _ref_init()
+    value = n * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "boxes/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: %d-frame vid, %d boxes/frame, %d classes, NMS IoU %.1f + link; "
+                               "each step = a %d-frame sample of it" % (T_FRAMES, N_BOXES, N_CLASSES, NMS_THRESH, F),
+                   "frames_per_step": F},
+        "cpu_baseline": {"value": value, "unit": "boxes/s", "cores": cores, "kind": _REF["kind"],
+                         "sample": "%d frames per step over %d processes (multiprocessing, the reference's only "
+                                   "parallel primitive, utils/common.py:358-359)" % (F, cores)},
+        "e2e": {"value": value, "unit": "boxes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from vdetlib_b200 import ops, synth
+    from vdetlib_b200.dist import ShardedVideoPostProcessor
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            sys.stderr.write("bench.py --gpus %d must be launched with torch.distributed.run --nproc-per-node %d\n"
+                             % (args.gpus, args.gpus))
+            return 2
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    T, N, C = T_FRAMES, N_BOXES, N_CLASSES
+    K, W = args.steps, max(args.warmup, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # rotating input sets: every rank its own shard (seed by rank), NSETS copies with different data
+    sets = []
+    host0 = None
+    for k in range(NSETS):
+        b, s = synth.boxes_scores(T, N, C, seed=2000 + 100 * rank + k)
+        if k == 0:
+            host0 = (b, s)
+        sets.append((torch.from_numpy(b.reshape(-1, 4)).to(dev), torch.from_numpy(s.reshape(-1, C)).to(dev)))
+    pp = ShardedVideoPostProcessor(T, N, C, NMS_THRESH, dev)
+    seg = pp.pp.seg_offsets
+
+    for k in range(W):
+        out = pp.step_device(*sets[k % NSETS])
+    ops.raise_for_status(pp.pp.status)
+    kept_frac = float(out["keep_cnt"].sum().item()) / (T * N * C)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.2)
+
+    # ---- timed region: K steps, inputs resident in HBM -----------------------------------
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for k in range(K):
+        pp.step_device(*sets[k % NSETS])
+    ev1.record()
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    ms_step = ms_total / K
+    value = world * T * N / (ms_step / 1000.0)
+
+    # ---- per-kernel timing for the roofline (same launches, each kernel alone) -------------
+    def time_kernel(fn, reps):
+        fn(0)
+        torch.cuda.synchronize()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for k in range(reps):
+            fn(k)
+        b_.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b_) / reps
+
+    reps = max(K, 10)
+    ms_nms = time_kernel(lambda k: ops.nms_frames(sets[k % NSETS][0], sets[k % NSETS][1], seg, NMS_THRESH, N,
+                                                  want_mask=True, status=pp.pp.status), reps)
+    ms_link = time_kernel(lambda k: ops.link_frames(sets[k % NSETS][0], seg, N), reps)
+    hbm_peak, peak_src = measured_peaks()
+    bytes_nms = T * N * (16 + 4 * C) + T * N * C * (4 + 1) + 4 * T * C + 4 * (T + 1)
+    bytes_link = T * N * 16 + T * N * 8 + 4 * (T + 1)
+    if ms_nms >= ms_link:
+        dom, dom_ms, dom_bytes = "nms_frames_kernel", ms_nms, bytes_nms
+    else:
+        dom, dom_ms, dom_bytes = "link_frames_kernel", ms_link, bytes_link
+    achieved = dom_bytes / (dom_ms / 1000.0) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
+                "kernels_ms": {"nms_frames_kernel": ms_nms, "link_frames_kernel": ms_link},
+                "note": "the step's kernels are issue/latency bound (sort + greedy walk + N^2 pair IoUs per "
+                        "frame), not HBM bound; see DESIGN.md. The HBM-roofline kernel of BASELINE.json is "
+                        "iou_matrix_f32 (below)."}
+
+    # ---- the IoU-matrix kernel against HBM (BASELINE.json: "% HBM peak on IoU kernel") -----
+    A = 16384
+    bb, _ = synth.boxes_scores(1, A, 1, seed=77)
+    xa = torch.from_numpy(bb[0]).to(dev)
+    mat = torch.empty((A, A), dtype=torch.float32, device=dev)          # 1 GiB > L2
+    ms_iou = time_kernel(lambda k: ops.iou_matrix(xa, xa, out=mat), 10)
+    iou_bytes = 4 * A * A + 32 * A
+    iou_roof = {"kernel": "iou_matrix_f32_kernel", "shape": [A, A], "ms_per_launch": ms_iou,
+                "achieved": iou_bytes / (ms_iou / 1000.0) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": iou_bytes / (ms_iou / 1000.0) / 1e9 / hbm_peak, "bound": "hbm"}
+    del mat
+
+    # ---- e2e: host buffers in, host results out, through the public API --------------------
+    pp.pp.stage(*host0)
+    for _ in range(3):
+        pp.step_host()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for k in range(K):
+        res = pp.step_host()
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / K
+    e2e = {"value": world * T * N / (e2e_ms / 1000.0), "unit": "boxes/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": pp.pp.h2d_bytes, "d2h_bytes_per_step": pp.pp.d2h_bytes,
+           "api": "vdetlib_b200.dist.ShardedVideoPostProcessor.step_host (pinned host buffers)"}
+    assert int(res["keep_cnt"].sum()) > 0
+
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "boxes/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: %d-frame synthetic vid proto, %d boxes/frame, %d VID classes, "
+                                   "NMS IoU %.1f (all classes, class-shared boxes) + frame-to-frame link, per GPU"
+                                   % (T, N, C, NMS_THRESH),
+                       "frames_per_gpu": T, "boxes_per_frame": N, "classes": C,
+                       "parallelism": "frames sharded over %d GPU(s); 1 all-gather of boundary boxes per step" % world,
+                       "l2": "rotating %d input sets (%.0f MB in + %.0f MB out per step) so that reuse distance "
+                             "> 126 MB L2" % (NSETS, (T * N * (16 + 4 * C)) / 1e6, (T * N * C * 5 + T * N * 8) / 1e6)},
+            "box_class_instances_per_s": value * C,
+            "kept_fraction": kept_frac,
+            "roofline": roofline, "iou_matrix_roofline": iou_roof,
+            "e2e": e2e, "gpu_launches": 2 * K, "clocks": clocks,
+        }
+        if world == 1:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

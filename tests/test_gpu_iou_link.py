@@ -1,0 +1,111 @@
+"""GPU parity: dense IoU (f64 = utils/common.py:451-468 bit for bit; f32 = nms.pyx pair
+arithmetic bit for bit), the suppression bit matrix, and the frame-to-frame link."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle, oracle_np
+from vdetlib_b200 import ops, synth
+from vdetlib_b200.utils.common import iou as gpu_iou
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def test_iou_f64_golden_and_types():
+    g = helpers.golden_npz("arrays.npz")
+    got = gpu_iou(g["iou_a_int"], g["iou_b_int"])
+    assert got.dtype == np.float64 and np.array_equal(got, g["iou_int"])
+    assert np.array_equal(gpu_iou(g["iou_a_f"], g["iou_b_f"]), g["iou_f"])
+    assert np.array_equal(gpu_iou([[0, 0, 9, 9]], [[9, 0, 18, 9], [0, 0, 9, 9]]), [[10.0 / 190.0, 1.0]])
+    with pytest.raises(IndexError):
+        gpu_iou([[0, 0, 9, 9]], np.asarray([]))        # reference fails on the 1-D empty array too
+
+
+@pytest.mark.parametrize("na,nb", [(1, 1), (1, 300), (37, 129), (64, 1024), (33, 1027), (200, 2050)])
+def test_iou_matrix_vs_oracle(na, nb):
+    rng = np.random.default_rng(na * 7 + nb)
+    a = rng.uniform(0, 500, (na, 4)); a[:, 2:] += a[:, :2]
+    b = rng.uniform(0, 500, (nb, 4)); b[:, 2:] += b[:, :2]
+    want64 = oracle_np.iou(a, b)
+    got64 = ops.iou_matrix(torch.from_numpy(a).to(DEV), torch.from_numpy(b).to(DEV)).cpu().numpy()
+    assert np.array_equal(got64, want64)
+    a32, b32 = a.astype(np.float32), b.astype(np.float32)
+    want32 = c_oracle.pair_iou_f32(a32, b32)
+    got32 = ops.iou_matrix(torch.from_numpy(a32).to(DEV), torch.from_numpy(b32).to(DEV)).cpu().numpy()
+    assert np.array_equal(got32, want32)
+    # float32 scores within 1e-5 of the float64 reference (north_star tolerance)
+    assert np.abs(got32.astype(np.float64) - oracle_np.iou(a32, b32)).max() <= 1e-5
+
+
+def test_iou_matrix_large_roundtrip_property():
+    """At roofline size (8192 x 8192) check symmetry and the diagonal instead of the oracle."""
+    b, _ = synth.boxes_scores(1, 8192, 1, seed=5)
+    x = torch.from_numpy(b[0]).to(DEV)
+    m = ops.iou_matrix(x, x)
+    assert torch.equal(m, m.t())
+    assert bool((m.diagonal() == 1.0).all())
+    sub = c_oracle.pair_iou_f32(b[0, :64], b[0, 4000:4100])
+    assert np.array_equal(m[:64, 4000:4100].cpu().numpy(), sub)
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 300, 1000])
+def test_bitmask_vs_oracle(n):
+    b, _ = synth.boxes_scores(1, n, 1, seed=n)
+    for thr in (0.3, 0.5):
+        mask, status = ops.iou_bitmask(torch.from_numpy(b[0]).to(DEV), thr)
+        assert int(status.item()) == 0
+        assert np.array_equal(mask.cpu().numpy().view(np.uint32), c_oracle.iou_bitmask(b[0], thr))
+
+
+def _link_oracle_packed(b, counts):
+    T, nmax = b.shape[:2]
+    succ, best = c_oracle.link_f32(b, counts)
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    ws, wb = [], []
+    for t in range(T - 1):
+        s = succ[t, :counts[t]].astype(np.int64)
+        ws.append(np.where(s >= 0, s + off[t + 1], -1))
+        wb.append(best[t, :counts[t]])
+    return np.concatenate(ws) if ws else np.zeros(0, np.int64), np.concatenate(wb) if wb else np.zeros(0, np.float32), off
+
+
+@pytest.mark.parametrize("T,N", [(2, 1), (5, 63), (4, 300), (3, 1000), (3, 1500)])
+def test_link_vs_oracle(T, N):
+    b, _ = synth.boxes_scores(T, N, 1, seed=T + N)
+    counts = np.full(T, N, np.int32)
+    want_s, want_b, off = _link_oracle_packed(b, counts)
+    db = torch.from_numpy(b.reshape(-1, 4)).to(DEV)
+    seg = ops.seg_offsets_uniform(T, N, torch.device(DEV))
+    succ, best = ops.link_frames(db, seg, N)
+    n_linked = (T - 1) * N
+    assert np.array_equal(succ.cpu().numpy()[:n_linked], want_s)
+    assert np.array_equal(best.cpu().numpy()[:n_linked], want_b)
+    assert bool((succ[n_linked:] == -1).all()) and bool((best[n_linked:] == 0).all())   # no halo
+    # within 1e-5 of the float64 IoU of the chosen successor
+    f64 = oracle_np.iou(b[0], b[1])
+    assert np.abs(best.cpu().numpy()[:N] - f64.max(axis=1)).max() <= 1e-5
+
+
+def test_link_ragged_and_halo():
+    counts = np.asarray([40, 0, 17, 300, 1, 64], np.int32)
+    T, nmax = len(counts), 300
+    b, _ = synth.boxes_scores(T + 1, nmax, 1, seed=9)
+    want_s, want_b, off = _link_oracle_packed(b[:T], counts)
+    rows = np.concatenate([b[t, :counts[t]] for t in range(T)])
+    dev = torch.device(DEV)
+    halo = b[T, :50]
+    succ, best = ops.link_frames(torch.from_numpy(rows).to(dev), torch.from_numpy(off.astype(np.int32)).to(dev),
+                                 int(counts.max()), torch.from_numpy(halo).to(dev))
+    n_linked = int(off[T - 1])
+    assert np.array_equal(succ.cpu().numpy()[:n_linked], want_s)
+    assert np.array_equal(best.cpu().numpy()[:n_linked], want_b)
+    # last frame vs the halo == a 2-frame link whose second frame is the halo
+    two = np.zeros((2, nmax, 4), np.float32)
+    two[0, :counts[-1]] = b[T - 1, :counts[-1]]
+    two[1, :50] = halo
+    hs, hb = c_oracle.link_f32(two, np.asarray([counts[-1], 50], np.int32))
+    assert np.array_equal(succ.cpu().numpy()[n_linked:], hs[0, :counts[-1]])
+    assert np.array_equal(best.cpu().numpy()[n_linked:], hb[0, :counts[-1]])

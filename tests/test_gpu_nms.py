@@ -1,0 +1,204 @@
+"""GPU parity of the NMS family against the oracle and the golden vectors (bit-exact indices).
+
+Every call goes through the C ABI of libvdet_b200.so (vdetlib_b200._lib / ops)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle
+from vdetlib_b200 import ops, synth
+from vdetlib_b200.utils import cython_nms as gpu
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def test_nms_golden_all():
+    g = helpers.golden_npz("nms.npz")
+    n = 0
+    for key in g.files:
+        if key.startswith("nms_") and "_keep_" in key:
+            tag, thr = key[4:].split("_keep_")
+            thr = int(thr) / (100.0 if len(thr) == 3 else 10.0)
+            got = gpu.nms(g["nms_%s_dets" % tag], thr)
+            assert got == g[key].tolist(), key
+            assert all(type(i) is int for i in got)
+            n += 1
+    assert n >= 18
+
+
+def test_vid_and_track_golden():
+    g = helpers.golden_npz("nms.npz")
+    for thr in (0.3, 0.5):
+        assert gpu.vid_nms(g["vid_dets"], thresh=thr) == g["vid_keep_%02d" % int(thr * 10)].tolist()
+        assert gpu.track_det_nms(g["tdn_tracks"], g["tdn_dets"], thr) == g["tdn_keep_%02d" % int(thr * 10)].tolist()
+
+
+def test_config1_300_boxes_thr05():
+    """BASELINE config 1: single 300-box frame, 1 class, IoU 0.5, bit-exact vs the CPU path."""
+    b, s = synth.boxes_scores(1, 300, 1, seed=1000)
+    dets = np.concatenate([b[0], s[0]], axis=1).astype(np.float32)
+    assert gpu.nms(dets, 0.5) == c_oracle.nms(dets, 0.5)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_nms_random_vs_oracle(seed):
+    rng = np.random.default_rng(100 + seed)
+    for _ in range(12):
+        n = int(rng.choice([1, 2, 31, 32, 33, 64, 65, 100, 257, 300, 512, 513, 777, 1024]))
+        thr = float(rng.choice([0.0, 0.1, 0.3, 0.5, 0.7, 0.95, 1.0]))
+        d = helpers.unique_score_dets(rng, n)
+        if rng.integers(0, 2):
+            d[:, :4] = np.round(d[:, :4])
+        assert gpu.nms(d, thr) == c_oracle.nms(d, thr), (n, thr)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_vid_nms_random_vs_oracle(seed):
+    rng = np.random.default_rng(200 + seed)
+    for _ in range(6):
+        n = int(rng.integers(1, 3000))
+        nf = int(rng.choice([1, 2, 7, 40]))
+        thr = float(rng.choice([0.1, 0.3, 0.5]))
+        v = helpers.unique_score_dets(rng, n, with_frame=nf)
+        if rng.integers(0, 2):
+            v[:, 0] = v[:, 0] * 3 + 1           # sparse frame ids
+        assert gpu.vid_nms(v, thr) == c_oracle.vid_nms(v, thr), (n, nf, thr)
+        q = int(rng.integers(0, 8))
+        t = helpers.unique_score_dets(rng, max(q, 1), with_frame=nf)[:q, :5]
+        assert gpu.track_det_nms(t, v, thr) == c_oracle.track_det_nms(t, v, thr), (n, nf, thr, q)
+
+
+def test_known_answers_and_errors():
+    d = np.asarray([[0, 0, 9, 9, 0.9], [9, 0, 18, 9, 0.8]], np.float32)
+    assert gpu.nms(d, 10.0 / 190.0) == [0]
+    assert gpu.nms(d, float(np.nextafter(np.float32(10.0 / 190.0), np.float32(1)))) == [0, 1]
+    assert gpu.nms(d, 0.7) == [0, 1]            # 0.7 is not a float32: the threshold rounds UP on the host
+    v = np.asarray([[1, 0, 0, 9, 9, 0.9], [2, 0, 0, 9, 9, 0.8], [1, 0, 0, 9, 9, 0.7]], np.float32)
+    assert gpu.vid_nms(v, 0.3) == [0, 1]
+    t = np.asarray([[1, 0, 0, 9, 9]], np.float32)
+    dd = np.asarray([[1, 0, 0, 9, 9, 0.9], [1, 50, 50, 60, 60, 0.5], [1, 51, 51, 60, 60, 0.4],
+                     [2, 0, 0, 9, 9, 0.3]], np.float32)
+    assert gpu.track_det_nms(t, dd, 0.3) == [1, 3]
+    assert gpu.nms(np.zeros((0, 5), np.float32), 0.3) == []
+    assert gpu.vid_nms(np.zeros((0, 6), np.float32), 0.3) == []
+    assert gpu.track_det_nms(t, np.zeros((0, 6), np.float32), 0.3) == []
+    assert gpu.track_det_nms(np.zeros((0, 5), np.float32), dd, 0.3) == c_oracle.track_det_nms(
+        np.zeros((0, 5), np.float32), dd, 0.3)
+    with pytest.raises(ValueError):
+        gpu.nms(d.astype(np.float64), 0.3)
+    with pytest.raises(ValueError):
+        gpu.nms(d[0], 0.3)
+    with pytest.raises(TypeError):
+        gpu.nms(d.tolist(), 0.3)
+    z = np.asarray([[5, 5, 4, 4, 0.9], [7, 7, 6, 6, 0.8]], np.float32)
+    with pytest.raises(ZeroDivisionError):
+        gpu.nms(z, 0.3)
+    # a zero-union pair that the reference never visits (j is suppressed first) must NOT raise
+    z2 = np.asarray([[0, 0, 20, 20, 0.9], [5, 5, 4, 4, 0.8], [7, 7, 6, 6, 0.7], [100, 100, 120, 120, 0.6]], np.float32)
+    try:
+        want = c_oracle.nms(z2, 0.3)
+    except ZeroDivisionError:
+        want = ZeroDivisionError
+    if want is ZeroDivisionError:
+        with pytest.raises(ZeroDivisionError):
+            gpu.nms(z2, 0.3)
+    else:
+        assert gpu.nms(z2, 0.3) == want
+
+
+def test_strided_and_wide_input():
+    rng = np.random.default_rng(8)
+    big = helpers.unique_score_dets(rng, 120)
+    wide = np.zeros((120, 9), np.float32)
+    wide[:, ::2] = big
+    assert gpu.nms(wide[:, ::2], 0.4) == c_oracle.nms(big, 0.4)
+    extra = np.concatenate([big, np.ones((120, 3), np.float32)], axis=1)     # extra columns are ignored
+    assert gpu.nms(extra, 0.4) == c_oracle.nms(big, 0.4)
+
+
+@pytest.mark.parametrize("T,N,C,thr", [(17, 300, 30, 0.3), (5, 64, 1, 0.5), (9, 33, 7, 0.3), (3, 1000, 4, 0.3)])
+def test_nms_frames_vs_oracle(T, N, C, thr):
+    b, s = synth.boxes_scores(T, N, C, seed=T * 1000 + N)
+    km, ki, kc = c_oracle.nms_frames(b, s, thr)
+    dev = torch.device("cuda")
+    db = torch.from_numpy(b.reshape(-1, 4)).to(dev)
+    ds = torch.from_numpy(s.reshape(-1, C)).to(dev)
+    seg = ops.seg_offsets_uniform(T, N, dev)
+    keep_idx, keep_cnt, keep_mask, status = ops.nms_frames(db, ds, seg, thr, N, want_mask=True)
+    assert ops.raise_for_status(status) == 0
+    keep_cnt = keep_cnt.cpu().numpy()            # [C, T]
+    assert np.array_equal(keep_cnt.T, kc)
+    gi = keep_idx.cpu().numpy().reshape(C, T, N)
+    gm = keep_mask.cpu().numpy().reshape(C, T, N)
+    for t in range(T):
+        for c in range(C):
+            want = ki[t, c]
+            want = np.where(want >= 0, want + t * N, -1)
+            assert np.array_equal(gi[c, t], want), (t, c)
+    assert np.array_equal(gm.transpose(1, 0, 2), km)
+    # class-major score layout gives the same answer
+    ds_cm = ds.t().contiguous()
+    keep_idx2, keep_cnt2, _, _ = ops.nms_frames(db, ds_cm, seg, thr, N, class_major=True)
+    assert torch.equal(keep_idx2, keep_idx) and torch.equal(keep_cnt2.cpu(), torch.from_numpy(keep_cnt))
+
+
+def test_nms_frames_ragged():
+    rng = np.random.default_rng(5)
+    counts = np.asarray([0, 1, 40, 0, 300, 33, 64, 2], np.int32)
+    T, nmax, C = len(counts), 300, 3
+    b, s = synth.boxes_scores(T, nmax, C, seed=77)
+    km, ki, kc = c_oracle.nms_frames(b, s, 0.3, counts)
+    rows_b = np.concatenate([b[t, :counts[t]] for t in range(T)])
+    rows_s = np.concatenate([s[t, :counts[t]] for t in range(T)])
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    dev = torch.device("cuda")
+    keep_idx, keep_cnt, keep_mask, status = ops.nms_frames(
+        torch.from_numpy(rows_b).to(dev), torch.from_numpy(rows_s).to(dev),
+        torch.from_numpy(off).to(dev), 0.3, int(counts.max()), want_mask=True)
+    assert ops.raise_for_status(status) == 0
+    assert np.array_equal(keep_cnt.cpu().numpy().T, kc)
+    gi = keep_idx.cpu().numpy()
+    gm = keep_mask.cpu().numpy()
+    for t in range(T):
+        for c in range(C):
+            n = counts[t]
+            want = ki[t, c, :n]
+            want = np.where(want >= 0, want + off[t], -1)
+            assert np.array_equal(gi[c, off[t]:off[t] + n], want)
+            assert np.array_equal(gm[c, off[t]:off[t] + n], km[t, c, :n])
+
+
+def test_full_config2_properties():
+    """BASELINE config 2 (1000 frames x 300 boxes x 30 classes): size-independent properties plus
+    an oracle check on a sample of frames."""
+    T, N, C, thr = 1000, 300, 30, 0.3
+    b, s = synth.boxes_scores(T, N, C, seed=2)
+    dev = torch.device("cuda")
+    db = torch.from_numpy(b.reshape(-1, 4)).to(dev)
+    ds = torch.from_numpy(s.reshape(-1, C)).to(dev)
+    seg = ops.seg_offsets_uniform(T, N, dev)
+    keep_idx, keep_cnt, keep_mask, status = ops.nms_frames(db, ds, seg, thr, N, want_mask=True)
+    assert ops.raise_for_status(status) == 0
+    km = keep_mask.view(C, T, N)
+    assert torch.equal(km.sum(-1).to(torch.int32), keep_cnt)                  # counts == mask popcounts
+    ki = keep_idx.view(C, T, N)
+    valid = ki >= 0
+    assert torch.equal(valid.sum(-1).to(torch.int32), keep_cnt)
+    # kept rows listed in descending score
+    rows = ki.clamp(min=0).long()
+    sc = ds.t().reshape(C, T * N).gather(1, rows.reshape(C, -1)).view(C, T, N)
+    sc = torch.where(valid, sc, torch.full_like(sc, -1.0))
+    assert bool((sc[:, :, 1:] <= sc[:, :, :-1]).all())
+    # idempotence: NMS of the survivors keeps every survivor (per class, on a few classes)
+    for c in (0, 13, 29):
+        ds_c = torch.where(km[c].reshape(-1).bool(), ds[:, c], torch.full_like(ds[:, c], -1.0))
+        # suppressed rows get the lowest scores so they cannot influence survivors
+        k2, c2, m2, _ = ops.nms_frames(db, ds_c.contiguous(), seg, thr, N, want_mask=True)
+        assert bool((m2.view(T, N)[km[c].bool()] == 1).all())
+    # oracle on a sample of frames
+    sample = [0, 1, 499, 998, 999]
+    okm, oki, okc = c_oracle.nms_frames(b[sample], s[sample], thr)
+    assert np.array_equal(keep_cnt.cpu().numpy().T[sample], okc)
+    assert np.array_equal(km.cpu().numpy().transpose(1, 0, 2)[sample], okm)

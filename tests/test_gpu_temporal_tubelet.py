@@ -1,0 +1,211 @@
+"""GPU parity: temporal score smoothing, spatial max-pooling, greedy tubelet proposal, top-k --
+through the reference-named adapters (vdetlib_b200.vdet.*) against the golden protos generated
+from the reference, and through the tensor ops against the NumPy oracle."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle_np
+from vdetlib_b200 import ops, synth
+from vdetlib_b200.vdet import tubelet_cls, track, video_det, image_det
+from vdetlib_b200.vdet.dataset import imagenet_vdet_classes as CLASSES
+from vdetlib_b200.utils.protocol import det_score
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+# ---- completion / max-pool / conv ----------------------------------------------------------
+def test_completion_and_maxpool_golden_f64():
+    g = helpers.golden_npz("arrays.npz")
+    rows = torch.from_numpy(g["rows_in"].copy()).to(DEV)
+    status = ops.score_completion_(rows)
+    assert ops.raise_for_status(status) == 0
+    assert np.array_equal(rows.cpu().numpy(), g["rows_completed"])
+    for w in (3, 5, 9, 201):
+        out = ops.temporal_maxpool(rows, w)
+        assert np.array_equal(out.cpu().numpy(), g["rows_maxpool_%d" % w])
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("L", [1, 2, 31, 257, 1024, 1025, 4999])
+def test_temporal_random_vs_oracle(dtype, L):
+    K = 9
+    x = synth.score_rows(K, L, seed=L, missing_frac=0.3, dtype=dtype, max_run=11)
+    lens = np.asarray([L, max(L // 2, 1), L, 1, L, max(L - 1, 1), L, L, max(L // 3, 1)], np.int32)
+    dx = torch.from_numpy(x.copy()).to(DEV)
+    dl = torch.from_numpy(lens).to(DEV)
+    # completion (in place, ragged).  float64 rows are bit-exact; float32 rows use float32 arithmetic
+    valid_rows = [k for k in range(K) if (x[k, :lens[k]] > -10).any()]
+    st = ops.score_completion_(dx, dl)
+    got = dx.cpu().numpy()
+    for k in valid_rows:
+        want = oracle_np.completion_row(x[k, :lens[k]].astype(np.float64))
+        if dtype == np.float64:
+            assert np.array_equal(got[k, :lens[k]], want)
+        else:
+            assert np.allclose(got[k, :lens[k]], want, rtol=0, atol=1e-5)
+        assert np.array_equal(got[k, lens[k]:], x[k, lens[k]:])            # beyond the row: untouched
+    if len(valid_rows) < K:
+        with pytest.raises(IndexError):
+            ops.raise_for_status(st)
+    # max-pool on the completed rows
+    for w in (3, 9):
+        out = ops.temporal_maxpool(dx, w, dl).cpu().numpy()
+        for k in range(K):
+            want = oracle_np.temporal_maxpool_row(got[k, :lens[k]].astype(np.float64), w)
+            assert np.array_equal(out[k, :lens[k]].astype(np.float64), want)
+    # depthwise conv, both paddings, bit-exact vs the separate mul/add restatement
+    taps = synth.gaussian_taps(3, 9, dtype=dtype)
+    taps[1] *= 0.5
+    for mode in ("zero", "edge"):
+        out = ops.temporal_conv1d(dx, torch.from_numpy(taps).to(DEV), mode, dl).cpu().numpy()
+        for k in range(K):
+            want = oracle_np.temporal_conv1d(got[k:k + 1, :lens[k]], taps[k % 3:k % 3 + 1], mode)
+            assert np.array_equal(out[k, :lens[k]], want[0]), (k, mode)
+
+
+def test_temporal_errors_and_all_missing():
+    x = torch.full((2, 10), -1e5, dtype=torch.float64, device=DEV)
+    x[1, 4] = 0.5
+    st = ops.score_completion_(x)
+    with pytest.raises(IndexError):
+        ops.raise_for_status(st)
+    assert bool((x[1] == 0.5).all()) and bool((x[0] == -1e5).all())
+    with pytest.raises(ValueError):
+        ops.temporal_maxpool(x, 4)
+
+
+def test_config4_shape_properties():
+    """BASELINE config 4 shape (30 classes x 10000-frame tubelets), reduced tubelet count:
+    properties that hold at any size."""
+    K, L = 4 * 30, 10000
+    x = synth.score_rows(K, L, seed=4, missing_frac=0.05)
+    dx = torch.from_numpy(x.copy()).to(DEV)
+    ops.raise_for_status(ops.score_completion_(dx))
+    done = dx.clone()
+    assert bool((done > -10).all())
+    assert bool((done[torch.from_numpy(x > -10).to(DEV)] == torch.from_numpy(x[x > -10]).to(DEV)).all())
+    ops.score_completion_(dx)
+    assert torch.equal(dx, done)                                              # idempotent
+    m3 = ops.temporal_maxpool(done, 3)
+    m9 = ops.temporal_maxpool(done, 9)
+    assert bool((m3 >= done).all()) and bool((m9 >= m3).all())
+    assert torch.equal(ops.temporal_maxpool(ops.temporal_maxpool(done, 3), 3), ops.temporal_maxpool(done, 5))
+    ident = torch.zeros((1, 9), dtype=torch.float32, device=DEV); ident[0, 4] = 1.0
+    assert torch.equal(ops.temporal_conv1d(done, ident), done)                # conv with a delta = identity
+    # oracle on two rows
+    for k in (0, K - 1):
+        assert np.allclose(done[k].cpu().numpy(), oracle_np.completion_row(x[k].astype(np.float64)), rtol=0, atol=1e-5)
+
+
+# ---- proto-level adapters vs golden protos -------------------------------------------------
+def _inputs():
+    p = helpers.golden_protos()
+    T, N, C = 8, 40, 5
+    boxes, scores = synth.boxes_scores(T, N, C, seed=4000, integer=True, frame_offset=1e-4)
+    return p, boxes, scores
+
+
+def test_spatial_max_pooling_protos_golden():
+    p, boxes, scores = _inputs()
+    vid, det, trk, out = p["vid"], p["det"], p["track"], p["out"]
+    for cls in (1, 3):
+        for suffix, thr in (("", 0.7), ("_05", 0.5)):
+            trk_in = copy.deepcopy(trk)
+            got = tubelet_cls.dets_spatial_max_pooling(vid, trk_in, copy.deepcopy(det), cls, overlap_thres=thr)
+            assert got == out["smp_%d%s" % (cls, suffix)]
+            assert trk_in == trk                                  # the track proto is not mutated
+        got = tubelet_cls.anchor_propagate(vid, copy.deepcopy(p["anchor_track"]), copy.deepcopy(det), cls)
+        assert got == out["anchor_%d" % cls]
+    f2d = {t + 1: (boxes[t].astype(np.float64), scores[t].astype(np.float64)) for t in range(8)}
+    got = tubelet_cls.raw_dets_spatial_max_pooling(vid, copy.deepcopy(trk), f2d, 2)
+    assert got == out["raw_smp_2"]
+
+
+def test_score_proto_functions():
+    g = helpers.golden_npz("arrays.npz")
+    rows = g["rows_in"]
+    sp = {'video': 'v', 'method': 'm',
+          'tubelets': [{'gt': 0, 'boxes': [{'det_score': float(v)} for v in r]} for r in rows]}
+    tubelet_cls.do_score_completion(sp)
+    assert np.array_equal(np.asarray(helpers.tubelet_scores(sp)), g["rows_completed"])
+    for w in (3, 9):
+        sp2 = copy.deepcopy(sp)
+        out = tubelet_cls.score_proto_temporal_maxpool(sp2, w)
+        assert np.array_equal(np.asarray(helpers.tubelet_scores(out)), g["rows_maxpool_%d" % w])
+        assert out['method'] == 'm_temporal_maxpool_%d' % w
+        assert out['tubelets'] is sp2['tubelets']                 # shallow copy, input mutated (:393)
+    assert tubelet_cls.score_proto_temporal_maxpool(sp, 1) is sp
+    with pytest.raises(ValueError):
+        tubelet_cls.score_proto_temporal_maxpool(sp, 4)
+    spg = copy.deepcopy(sp); spg['tubelets'][2]['gt'] = 1
+    with pytest.raises(ValueError):
+        tubelet_cls.score_proto_temporal_maxpool(spg, 3)
+    bad = {'video': 'v', 'method': 'm', 'tubelets': [{'gt': 0, 'boxes': [{'det_score': -1e5}, {'det_score': -1e5}]}]}
+    with pytest.raises(IndexError):
+        tubelet_cls.do_score_completion(bad)
+    # temporal convolution stand-in: equals the NumPy restatement
+    net = tubelet_cls.TemporalConvNet({'det_scores': [0.25, 0.5, 0.25]}, bias=0.1)
+    out = tubelet_cls.score_conv_cls(copy.deepcopy(sp), net)
+    for t_in, t_out in zip(sp['tubelets'], out['tubelets']):
+        x = np.asarray([[b['det_score'] for b in t_in['boxes']]])
+        want = oracle_np.temporal_conv1d(x, np.asarray([[0.25, 0.5, 0.25]])) + 0.1
+        assert np.array_equal(np.asarray([b['conv_score'] for b in t_out['boxes']]), want[0])
+
+
+def test_vid_nms_and_image_nms_protos_golden():
+    p, boxes, scores = _inputs()
+    det, out = p["det"], p["out"]
+    for cls in (1, 3):
+        det_in = copy.deepcopy(det)
+        kept = video_det.apply_vid_nms(det_in, cls)
+        assert [d['hash'] for d in kept['detections']] == out["vid_nms_%d" % cls]
+        assert all(any(k is d for d in det_in['detections']) for k in kept['detections'][:5])   # same objects
+    assert image_det.apply_image_nms(boxes[0].astype(np.float64), scores[0, :, 0].astype(np.float64), 0.4) == out["image_nms"]
+
+
+def test_greedy_tracking_golden():
+    p, boxes, scores = _inputs()
+    vid, det, out = p["vid"], p["det"], p["out"]
+    opts = helpers.Opts(max_tracks=5, thres=0.5, nms_thres=0.3)
+    tp = track.greedily_track_from_det(vid, copy.deepcopy(det), helpers.fake_tracker, lambda d: det_score(d, 2), opts)
+    assert tp == out["greedy_det"]
+    T, N, C = 8, 40, 5
+    det_info = np.concatenate([np.repeat(np.arange(1, T + 1), N)[:, None].astype(np.float64),
+                               boxes.reshape(-1, 4).astype(np.float64),
+                               scores.reshape(-1, C).astype(np.float64)], axis=1)
+    opts = helpers.Opts(max_tracks=4, thres=0.6, nms_thres=None)
+    tp = track.greedily_track_from_raw_dets(vid, det_info, helpers.fake_tracker, 3, opts)
+    assert tp == out["greedy_raw"]
+
+
+def test_greedy_tracking_keep_state_vs_oracle():
+    """Larger run: the surviving-detection set after every tracker call equals the oracle's."""
+    T, N, C = 30, 120, 3
+    boxes, scores = synth.boxes_scores(T, N, C, seed=31, integer=True, frame_offset=1e-5)
+    vid = synth.vid_proto(T)
+    det_info = np.concatenate([np.repeat(np.arange(1, T + 1), N)[:, None].astype(np.float64),
+                               boxes.reshape(-1, 4).astype(np.float64),
+                               scores.reshape(-1, C).astype(np.float64)], axis=1)
+    opts = helpers.Opts(max_tracks=12, thres=0.2, nms_thres=0.3)
+    want, _ = oracle_np.greedily_track_from_raw_dets(vid, det_info, helpers.fake_tracker, 2, opts)
+    got = track.greedily_track_from_raw_dets(vid, det_info, helpers.fake_tracker, 2, opts)
+    assert got == want
+
+
+def test_threshold_topk_vs_oracle():
+    rng = np.random.default_rng(13)
+    T, R, C = 6, 300, 8
+    scores = rng.permuted(np.tile(np.linspace(0.0, 0.4, R), (T, C, 1)), axis=-1).transpose(0, 2, 1).astype(np.float32)
+    scores[:, :, 3] *= 0.15                      # a class with few candidates (count <= cap path)
+    boxes = rng.uniform(0, 500, (T, R, 4 * C)).astype(np.float32)
+    got = video_det.threshold_topk_frames(scores, boxes, thresh=0.05, max_per_image=100)
+    for t in range(T):
+        want = oracle_np.threshold_topk_frame(scores[t], boxes[t], 0.05, 100)
+        for j in range(1, C):
+            assert np.array_equal(got[j][t], want[j]), (t, j)

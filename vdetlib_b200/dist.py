@@ -1,0 +1,97 @@
+"""Frame-sharded data parallelism: one process per GPU, torch.distributed over NCCL.
+
+Every stage of the hot path is independent per frame except the frame-to-frame link, where the
+last frame of rank r needs the boxes of the FIRST frame of rank r+1.  That is the only
+data-path collective: one all-gather of each rank's first-frame boxes (<= max_boxes*16 B + a
+count per rank -- latency-bound over NVSwitch), issued on a side stream so it overlaps the NMS
+kernel; the link kernel waits on it.  The reference has no distributed code at all
+(single process), so there is nothing to mirror here beyond the frame order.
+
+The exchange itself is backend-agnostic torch.distributed plumbing (NCCL on GPUs; the CPU
+tests drive it with gloo, world_size 2).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_frames, world_size, rank):
+    """Contiguous, balanced frame range [start, stop) of ``rank`` (earlier ranks take the remainder)."""
+    base, rem = divmod(int(n_frames), int(world_size))
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+class BoundaryExchange(object):
+    """All-gather of first-frame boxes; each rank reads its right neighbour's slot."""
+
+    def __init__(self, max_boxes, device, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.max_boxes = int(max_boxes)
+        self.device = torch.device(device)
+        # slot layout per rank: [max_boxes, 4] boxes then one row holding the count in [0,0]
+        self.send = torch.zeros((self.max_boxes + 1, 4), dtype=torch.float32, device=self.device)
+        self.recv = torch.zeros((self.world, self.max_boxes + 1, 4), dtype=torch.float32, device=self.device)
+
+    def start(self, first_frame_boxes):
+        """Enqueue the all-gather (async when the backend supports it); returns a handle."""
+        n = int(first_frame_boxes.shape[0])
+        if n > self.max_boxes:
+            raise ValueError("first frame has %d boxes > max_boxes %d" % (n, self.max_boxes))
+        self.send[:n].copy_(first_frame_boxes)
+        self.send[self.max_boxes, 0] = float(n)
+        if self.world == 1:
+            return None
+        return dist.all_gather_into_tensor(self.recv.view(-1, 4), self.send, group=self.group, async_op=True)
+
+    def finish(self, handle, count_hint=None):
+        """Wait and return the halo = boxes of the next rank's first frame (None on the last rank).
+
+        ``count_hint``: the neighbour's box count when it is known a priori (uniform frames);
+        avoids reading the count back from the device."""
+        if self.world == 1 or self.rank == self.world - 1:
+            if handle is not None:
+                handle.wait()
+            return None
+        handle.wait()
+        slot = self.recv[self.rank + 1]
+        n = int(count_hint) if count_hint is not None else int(slot[self.max_boxes, 0].item())
+        return slot[:n]
+
+
+class ShardedVideoPostProcessor(object):
+    """The per-rank step of the multi-GPU pipeline: NMS of the local frames, boundary exchange,
+    link (local frames + halo).  Weak scaling: every rank holds ``n_frames`` frames."""
+
+    def __init__(self, n_frames, n_boxes, n_classes, nms_thresh=0.3, device=None, group=None):
+        from .vdet.video_det import VideoPostProcessor
+        self.pp = VideoPostProcessor(n_frames, n_boxes, n_classes, nms_thresh, device)
+        self.exchange = BoundaryExchange(n_boxes, self.pp.device, group)
+        self.side = torch.cuda.Stream(device=self.pp.device)
+        self.n_boxes = n_boxes
+
+    def step_device(self, d_boxes, d_scores):
+        """Device-resident inputs; returns the result dict of VideoPostProcessor.run_device."""
+        from . import ops
+        pp = self.pp
+        main = torch.cuda.current_stream()
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            handle = self.exchange.start(d_boxes[:self.n_boxes])
+        keep_idx, keep_cnt, keep_mask, _ = ops.nms_frames(
+            d_boxes, d_scores, pp.seg_offsets, pp.nms_thresh, pp.N, want_mask=True, status=pp.status)
+        with torch.cuda.stream(self.side):
+            halo = self.exchange.finish(handle, count_hint=self.n_boxes)
+        main.wait_stream(self.side)
+        succ, link_iou = ops.link_frames(d_boxes, pp.seg_offsets, pp.N, halo)
+        return {"keep_idx": keep_idx, "keep_cnt": keep_cnt, "keep_mask": keep_mask,
+                "succ": succ, "link_iou": link_iou}
+
+    def step_host(self):
+        """The end-to-end step: H2D from the pinned staging buffers (fill them with
+        ``self.pp.stage(boxes, scores)``), kernels + boundary exchange, D2H of the results."""
+        pp = self.pp
+        pp.d_boxes.copy_(pp.h_boxes, non_blocking=True)
+        pp.d_scores.copy_(pp.h_scores, non_blocking=True)
+        return pp.read_back(self.step_device(pp.d_boxes, pp.d_scores))

@@ -116,6 +116,10 @@ class VideoPostProcessor(object):
         self.d_boxes.copy_(self.h_boxes, non_blocking=True)
         self.d_scores.copy_(self.h_scores, non_blocking=True)
         out = self.run_device(self.d_boxes, self.d_scores, halo)
+        return self.read_back(out)
+
+    def read_back(self, out):
+        """D2H of the results into the pinned buffers; synchronises and returns host views."""
         self.h_mask.copy_(out["keep_mask"], non_blocking=True)
         self.h_cnt.copy_(out["keep_cnt"], non_blocking=True)
         self.h_succ.copy_(out["succ"], non_blocking=True)
