@@ -123,7 +123,7 @@ def _ref_frames(job):
     return F * N
 
 
-def cpu_baseline(sample_frames=200):
+def cpu_baseline(sample_frames=1500):
     """Single-thread reference path on a bounded sample (rank 0, N=1 only)."""
     from vdetlib_b200 import synth
     _ref_init()

@@ -216,14 +216,11 @@ static size_t nms_smem_bytes(int nb, int n_classes, bool stage) {
 
 template <int NPER>
 static int launch_nms_frames(const NmsFramesParams& p, size_t smem, int grid, cudaStream_t st) {
-    static bool configured[64];
-    int dev = 0;
-    VDET_CUDA(cudaGetDevice(&dev));
-    if (!configured[dev & 63]) {
-        VDET_CUDA(cudaFuncSetAttribute(nms_frames_kernel<NPER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       max_optin_smem_cached()));
-        configured[dev & 63] = true;
+    if (smem > max_dynamic_smem(nms_frames_kernel<NPER>)) {
+        set_error("nms_frames: %zu bytes of shared memory needed", smem);
+        return VDET_ERR_UNSUPPORTED;
     }
+    VDET_CUDA(allow_dynamic_smem(nms_frames_kernel<NPER>, smem));
     nms_frames_kernel<NPER><<<grid, NMS_THREADS, smem, st>>>(p);
     VDET_LAUNCH_CHECK();
     return VDET_OK;
@@ -276,10 +273,6 @@ extern "C" int vdet_nms_frames_f32(const float* boxes, int box_ld,
     const size_t smem_stage = nms_smem_bytes(nb, n_classes, true);
     p.stage = (want_stage && smem_stage <= 100 * 1024) ? 1 : 0;
     const size_t smem = nms_smem_bytes(nb, n_classes, p.stage != 0);
-    if (smem > (size_t)max_optin_smem_cached()) {
-        set_error("nms_frames: %zu bytes of shared memory needed", smem);
-        return VDET_ERR_UNSUPPORTED;
-    }
     int per_sm = (int)((size_t)(220 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;

@@ -188,9 +188,8 @@ static int run_maxpool(const void* in, void* out, int64_t n_rows, int64_t L, int
                        int window, double pad, cudaStream_t st) {
     const int h = window / 2;
     const size_t smem = (size_t)(TP_TILE + 2 * h) * sizeof(T);
-    if (smem > (size_t)max_optin_smem_cached()) { set_error("temporal_maxpool: window %d too large", window); return VDET_ERR_UNSUPPORTED; }
-    if (smem > 48 * 1024)
-        VDET_CUDA(cudaFuncSetAttribute(temporal_maxpool_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > max_dynamic_smem(temporal_maxpool_kernel<T>)) { set_error("temporal_maxpool: window %d too large", window); return VDET_ERR_UNSUPPORTED; }
+    VDET_CUDA(allow_dynamic_smem(temporal_maxpool_kernel<T>, smem));
     const int64_t tiles = (L + TP_TILE - 1) / TP_TILE;
     const int64_t grid = tiles * n_rows;
     if (grid > 0x7fffffff) { set_error("temporal_maxpool: grid too large"); return VDET_ERR_UNSUPPORTED; }
@@ -205,9 +204,8 @@ static int run_conv(const void* in, void* out, int64_t n_rows, int64_t L, int64_
                     const void* taps, int n_channels, int window, int pad_mode, cudaStream_t st) {
     const int h = window / 2;
     const size_t smem = (size_t)(TP_TILE + 2 * h + window) * sizeof(T);
-    if (smem > (size_t)max_optin_smem_cached()) { set_error("temporal_conv1d: window %d too large", window); return VDET_ERR_UNSUPPORTED; }
-    if (smem > 48 * 1024)
-        VDET_CUDA(cudaFuncSetAttribute(temporal_conv1d_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > max_dynamic_smem(temporal_conv1d_kernel<T>)) { set_error("temporal_conv1d: window %d too large", window); return VDET_ERR_UNSUPPORTED; }
+    VDET_CUDA(allow_dynamic_smem(temporal_conv1d_kernel<T>, smem));
     const int64_t tiles = (L + TP_TILE - 1) / TP_TILE;
     const int64_t grid = tiles * n_rows;
     if (grid > 0x7fffffff) { set_error("temporal_conv1d: grid too large"); return VDET_ERR_UNSUPPORTED; }
@@ -223,13 +221,12 @@ static int run_completion(void* scores, int64_t n_rows, int64_t L, int64_t ld, c
                           double miss_thr, uint32_t* status, cudaStream_t st) {
     const int cap = (int)((L + 3) / 4 * 4);
     const size_t smem = (size_t)cap * (sizeof(T) + 2 * sizeof(int32_t));
-    if (smem > (size_t)max_optin_smem_cached()) {
+    if (smem > max_dynamic_smem(score_completion_kernel<T>)) {
         set_error("score_completion: rows of %lld elements exceed the shared-memory row limit of this build",
                   (long long)L);
         return VDET_ERR_UNSUPPORTED;
     }
-    VDET_CUDA(cudaFuncSetAttribute(score_completion_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   max_optin_smem_cached()));
+    VDET_CUDA(allow_dynamic_smem(score_completion_kernel<T>, smem));
     if (n_rows > 0x7fffffff) { set_error("score_completion: too many rows"); return VDET_ERR_UNSUPPORTED; }
     score_completion_kernel<T><<<(unsigned)n_rows, CP_THREADS, smem, st>>>((T*)scores, L, ld, lengths, (T)miss_thr,
                                                                            cap, status);
