@@ -118,7 +118,8 @@ def test_strided_and_wide_input():
     assert gpu.nms(extra, 0.4) == c_oracle.nms(big, 0.4)
 
 
-@pytest.mark.parametrize("T,N,C,thr", [(17, 300, 30, 0.3), (5, 64, 1, 0.5), (9, 33, 7, 0.3), (3, 1000, 4, 0.3)])
+@pytest.mark.parametrize("T,N,C,thr", [(17, 300, 30, 0.3), (5, 64, 1, 0.5), (9, 33, 7, 0.3), (3, 1000, 4, 0.3),
+                                        (3, 1025, 2, 0.3), (160, 2000, 3, 0.3), (2, 2048, 2, 0.5)])
 def test_nms_frames_vs_oracle(T, N, C, thr):
     b, s = synth.boxes_scores(T, N, C, seed=T * 1000 + N)
     km, ki, kc = c_oracle.nms_frames(b, s, thr)
@@ -202,3 +203,17 @@ def test_full_config2_properties():
     okm, oki, okc = c_oracle.nms_frames(b[sample], s[sample], thr)
     assert np.array_equal(keep_cnt.cpu().numpy().T[sample], okc)
     assert np.array_equal(km.cpu().numpy().transpose(1, 0, 2)[sample], okm)
+
+
+def test_nms_any_length_frames():
+    """Frames longer than the bit-matrix kernels hold (> 2048 boxes) take the on-the-fly path."""
+    rng = np.random.default_rng(41)
+    d = helpers.unique_score_dets(rng, 5000, scale=900.0)
+    assert gpu.nms(d, 0.3) == c_oracle.nms(d, 0.3)
+    v = helpers.unique_score_dets(rng, 9000, with_frame=3, scale=900.0)
+    assert gpu.vid_nms(v, 0.5) == c_oracle.vid_nms(v, 0.5)
+    t = helpers.unique_score_dets(rng, 4, with_frame=3)[:, :5]
+    assert gpu.track_det_nms(t, v, 0.3) == c_oracle.track_det_nms(t, v, 0.3)
+    z = np.concatenate([d[:3000], np.asarray([[5, 5, 4, 4, 0.001], [7, 7, 6, 6, 0.0005]], np.float32)])
+    with pytest.raises(ZeroDivisionError):
+        gpu.nms(z, 0.3)

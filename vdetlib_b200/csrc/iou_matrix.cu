@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(256) iou_bitmask_kernel(const float4* __restri
         const float4 bj = __ldg(boxes + j);
         float inter, uni;
         inter_union_f32(bi, ai, bj, area_f32(bj), inter, uni);
-        if (__fdiv_rn(inter, uni) >= T) word |= (1u << jj);
+        if (iou_ge(inter, uni, T)) word |= (1u << jj);
         zero |= (uni == 0.0f) && (i != j) && (i < n);
     }
     if (i < n) mask[(int64_t)i * W + cb] = word;

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(LINK_THREADS) link_frames_kernel(const float4*
         for (int j = 0; j < cnt; ++j) {
             float inter, uni;
             inter_union_f32(bi, ai, s_box[j], s_area[j], inter, uni);
-            const float v = __fdiv_rn(inter, uni);
+            const float v = iou_quotient(inter, uni);
             // NaN (0/0) and union==0 never win; strict '>' keeps the FIRST maximum
             if (uni != 0.0f && v > best) { best = v; arg = j0 + j; }
         }

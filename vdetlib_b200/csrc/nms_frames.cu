@@ -35,10 +35,34 @@ struct NmsFramesParams {
     uint32_t* status;
     int nb;        // padded frame capacity (multiple of 32)
     int stage;     // 1: scores transposed into shared memory
+    uint32_t* gmask;   // big-frame variant: per-CTA bit-matrix slots in global memory
+    int npad;          // big-frame variant: power-of-two sort length >= nb
 };
 
+// Exact ZeroDivisionError test of nms.pyx:64 (cold path, only for frames that contain a
+// zero-union pair at all): the pair (ci, j) is visited by the reference iff j comes later in the
+// score order and is not yet removed when ci is kept.  `so` is the warp's striped order scratch.
+__device__ __noinline__ void zero_division_check(const uint32_t* so, int ngroups, const float4* sbox,
+                                                 const float* sarea, uint32_t rem, uint32_t ci, int pos, int n,
+                                                 int lane, uint32_t* status) {
+    const float4 bi = sbox[ci];
+    const float ai = sarea[ci];
+    bool zd = false;
+    for (int g2 = 0; g2 < ngroups; ++g2) {
+        const int pos2 = g2 * 32 + lane;
+        const uint32_t j = pos2 < n ? so[g2 * 33 + lane] : 0u;
+        const uint32_t wj = __shfl_sync(FULL, rem, (int)((j >> 5) & 31));
+        if (pos2 > pos && pos2 < n && !((wj >> (j & 31)) & 1u)) {
+            float inter, uni;
+            inter_union_f32(bi, ai, sbox[j], sarea[j], inter, uni);
+            zd |= (uni == 0.0f);
+        }
+    }
+    if (__any_sync(FULL, zd) && lane == 0) atomicOr(status, VDET_STATUS_ZERO_DIVISION);
+}
+
 template <int NPER>
-__global__ void __launch_bounds__(NMS_THREADS) nms_frames_kernel(const NmsFramesParams p) {
+__global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 2 : 1)) nms_frames_kernel(const NmsFramesParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NB = p.nb;
     const int W = NB >> 5;          // mask words per row (<= 32 in this variant)
@@ -48,7 +72,8 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_frames_kernel(const NmsFrames
     float* sarea = reinterpret_cast<float*>(sbox + NB);
     int32_t* srow = reinterpret_cast<int32_t*>(sarea + NB);
     uint32_t* smask = reinterpret_cast<uint32_t*>(srow + NB);
-    float* sscore = reinterpret_cast<float*>(smask + (size_t)NB * WS);
+    uint32_t* sord = smask + (size_t)NB * WS;                       // [NMS_WARPS][NPER*33] walk-order scratch
+    float* sscore = reinterpret_cast<float*>(sord + NMS_WARPS * NPER * 33);
     __shared__ int s_zero_union;
 
     const int tid = threadIdx.x;
@@ -113,8 +138,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_frames_kernel(const NmsFrames
                     const float aj = sarea[j];
                     float inter, uni;
                     inter_union_f32(bi, ai, bj, aj, inter, uni);
-                    const float ovr = __fdiv_rn(inter, uni);
-                    if (ovr >= T) word |= (1u << jj);
+                    if (iou_ge(inter, uni, T)) word |= (1u << jj);
                     zero |= (uni == 0.0f) && (i != j) && (i < n) && (j < n);
                 }
                 // columns beyond the frame never suppress / are never visited
@@ -144,45 +168,53 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_frames_kernel(const NmsFrames
             }
             warp_bitonic_sort<NPER>(key, lane);
 
+            // blocked (sort) -> striped (walk) layout of the sorted indices through this warp's
+            // shared scratch: ord[g] = index at sorted position g*32 + lane.  The +p/32 skew
+            // makes both the blocked writes and the striped reads conflict-free.
+            uint32_t ord[NPER];
+            {
+                uint32_t* so = sord + warp * (NPER * 33);
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < NPER; ++r) {
+                    const int pp = lane * NPER + r;
+                    so[pp + (pp >> 5)] = (uint32_t)key[r];
+                }
+                __syncwarp();
+#pragma unroll
+                for (int g = 0; g < NPER; ++g) ord[g] = so[g * 33 + lane];
+            }
+
             uint32_t rem = 0;        // lane w: word w of the removed set
             uint32_t kept = 0;       // lane w: word w of the kept set
             int cnt = 0;
             int32_t buf = -1;        // lane (cnt & 31) buffers the cnt-th kept row
             int32_t* out_idx = p.keep_idx + (int64_t)c * p.n_rows + off;
-            for (int src = 0; src < 32; ++src) {
-                if (src * NPER >= n) break;
+            // Greedy walk, 32 candidates per step: every lane tests its own candidate against the
+            // removed set, a ballot gives the alive ones; the lowest alive lane is by construction
+            // the next kept box, its mask row is OR-ed in and kills later lanes of the same group.
 #pragma unroll
-                for (int r = 0; r < NPER; ++r) {
-                    const uint32_t i = __shfl_sync(FULL, (uint32_t)key[r], src);
-                    if (src * NPER + r < n) {                     // warp-uniform
-                        const uint32_t w = __shfl_sync(FULL, rem, (int)(i >> 5));
-                        if (!((w >> (i & 31)) & 1u)) {            // warp-uniform: i is kept
-                            if (check_zero) {
-                                // exact ZeroDivisionError test of nms.pyx:64: a pair (i, j) is
-                                // visited iff j comes later in the order and is not yet removed
-                                const int pos = src * NPER + r;
-                                const float4 bi = sbox[i];
-                                const float ai = sarea[i];
-                                bool zd = false;
-#pragma unroll
-                                for (int r2 = 0; r2 < NPER; ++r2) {
-                                    const uint32_t j = (uint32_t)key[r2];
-                                    const uint32_t wj = __shfl_sync(FULL, rem, (int)((j >> 5) & 31));
-                                    const int pos2 = lane * NPER + r2;
-                                    if (pos2 > pos && pos2 < n && !((wj >> (j & 31)) & 1u)) {
-                                        float inter, uni;
-                                        inter_union_f32(bi, ai, sbox[j], sarea[j], inter, uni);
-                                        zd |= (uni == 0.0f);
-                                    }
-                                }
-                                if (__any_sync(FULL, zd) && lane == 0) atomicOr(p.status, VDET_STATUS_ZERO_DIVISION);
-                            }
-                            if (lane < Wn) rem |= smask[i * WS + lane];
-                            if (lane == (int)(i >> 5)) kept |= (1u << (i & 31));
-                            if (lane == (cnt & 31)) buf = srow[i];
-                            ++cnt;
-                            if ((cnt & 31) == 0) out_idx[cnt - 32 + lane] = buf;
-                        }
+            for (int g = 0; g < NPER; ++g) {
+                if (g * 32 < n) {                                             // warp-uniform
+                    const uint32_t i = ord[g];
+                    const bool valid = (g * 32 + lane) < n;
+                    const uint32_t w = __shfl_sync(FULL, rem, (int)((i >> 5) & 31));
+                    unsigned alive = __ballot_sync(FULL, valid && !((w >> (i & 31)) & 1u));
+                    while (alive) {
+                        const int l = __ffs(alive) - 1;
+                        const uint32_t ci = __shfl_sync(FULL, i, l);          // the kept box
+                        if (check_zero)
+                            zero_division_check(sord + warp * (NPER * 33), NPER, sbox, sarea, rem, ci, g * 32 + l, n,
+                                                lane, p.status);
+                        const uint32_t roww = (lane < Wn) ? smask[ci * WS + lane] : 0u;
+                        rem |= roww;
+                        if (lane == (int)(ci >> 5)) kept |= (1u << (ci & 31));
+                        if (lane == (cnt & 31)) buf = srow[ci];
+                        ++cnt;
+                        if ((cnt & 31) == 0) out_idx[cnt - 32 + lane] = buf;
+                        const uint32_t wv = __shfl_sync(FULL, roww, (int)((i >> 5) & 31));
+                        alive &= ~__ballot_sync(FULL, (wv >> (i & 31)) & 1u);
+                        alive &= ~(1u << l);
                     }
                 }
             }
@@ -206,10 +238,11 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_frames_kernel(const NmsFrames
     }
 }
 
-static size_t nms_smem_bytes(int nb, int n_classes, bool stage) {
+static size_t nms_smem_bytes(int nb, int nper, int n_classes, bool stage) {
     const int W = nb / 32, WS = W | 1;
     size_t b = (size_t)nb * (sizeof(float4) + sizeof(float) + sizeof(int32_t));
     b += (size_t)nb * WS * sizeof(uint32_t);
+    b += (size_t)NMS_WARPS * nper * 33 * sizeof(uint32_t);
     if (stage) b += (size_t)n_classes * (nb + 1) * sizeof(float);
     return b;
 }
@@ -226,13 +259,188 @@ static int launch_nms_frames(const NmsFramesParams& p, size_t smem, int grid, cu
     return VDET_OK;
 }
 
+
+// ==========================================================================================
+// Big-frame variant: 1024 < max frame length <= 2048 (BASELINE config 5: 2000 boxes/frame).
+// Same three phases; what changes is where things live:
+//   * the bit matrix (N x N/32 words = 500 KB at N=2000) does not fit in shared memory: every
+//     persistent CTA owns a slot in a global scratch buffer, written with 32-byte-per-lane
+//     vector stores in phase B and read back (from L2) one 128/256-byte row per kept box;
+//   * the per-class sort runs per warp over a 64-bit key array in shared memory (bitonic,
+//     __syncwarp between steps) instead of registers;
+//   * the removed / kept sets take two words per lane.
+// ==========================================================================================
+constexpr int BIG_MAX = 2048;
+
+__global__ void __launch_bounds__(NMS_THREADS) nms_frames_big_kernel(const NmsFramesParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int NB = p.nb;            // multiple of 256 here (8 column words per tile)
+    const int W = NB >> 5;          // <= 64
+    const int NPAD = p.npad;
+    float4* sbox = reinterpret_cast<float4*>(smem_raw);
+    float* sarea = reinterpret_cast<float*>(sbox + NB);
+    int32_t* srow = reinterpret_cast<int32_t*>(sarea + NB);
+    uint64_t* skeys = reinterpret_cast<uint64_t*>(srow + NB);      // [NMS_WARPS][NPAD]
+    __shared__ int s_zero_union;
+    uint32_t* gmask = p.gmask + (size_t)blockIdx.x * NB * W;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = p.n_classes;
+    const float T = p.thresh_f32;
+    uint64_t* keys = skeys + (size_t)warp * NPAD;
+
+    for (int seg = blockIdx.x; seg < p.n_segs; seg += gridDim.x) {
+        const int off = p.seg_offsets[seg];
+        const int n = p.seg_offsets[seg + 1] - off;
+        if (n > NB) {
+            if (tid == 0) atomicOr(p.status, 0x80000000u);
+            continue;
+        }
+        if (tid == 0) s_zero_union = 0;
+        for (int e = tid; e < NB; e += NMS_THREADS) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            int32_t row = -1;
+            if (e < n) {
+                row = p.row_ids ? p.row_ids[off + e] : off + e;
+                b = load_box(p.boxes, row, p.box_ld, p.box_vec);
+            }
+            sbox[e] = b;
+            sarea[e] = area_f32(b);
+            srow[e] = row;
+        }
+        __syncthreads();
+        // ---- B: bit matrix into this CTA's global slot; tile = 32 rows x 8 words -----------
+        {
+            const int Wn = (n + 31) >> 5;
+            const int G = (Wn + 7) >> 3;                 // groups of 8 column words
+            const int ntiles = Wn * G;
+            for (int tile = warp; tile < ntiles; tile += NMS_WARPS) {
+                const int rb = tile / G, g = tile - rb * G;
+                const int i = rb * 32 + lane;
+                const float4 bi = sbox[i];
+                const float ai = sarea[i];
+                uint32_t words[8];
+                bool zero = false;
+#pragma unroll
+                for (int cw = 0; cw < 8; ++cw) {
+                    const int cb = g * 8 + cw;
+                    uint32_t word = 0;
+                    if (cb < Wn) {
+#pragma unroll 8
+                        for (int jj = 0; jj < 32; ++jj) {
+                            const int j = cb * 32 + jj;
+                            float inter, uni;
+                            inter_union_f32(bi, ai, sbox[j], sarea[j], inter, uni);
+                            if (iou_ge(inter, uni, T)) word |= (1u << jj);
+                            zero |= (uni == 0.0f) && (i != j) && (i < n) && (j < n);
+                        }
+                        const int valid = n - cb * 32;
+                        if (valid < 32) word &= (valid <= 0) ? 0u : ((1u << valid) - 1u);
+                    }
+                    words[cw] = word;
+                }
+                uint4* dst = reinterpret_cast<uint4*>(gmask + (size_t)i * W + g * 8);
+                dst[0] = make_uint4(words[0], words[1], words[2], words[3]);
+                dst[1] = make_uint4(words[4], words[5], words[6], words[7]);
+                if (__any_sync(FULL, zero) && lane == 0) s_zero_union = 1;
+            }
+        }
+        __syncthreads();      // block-scope visibility of this CTA's own global writes
+        const bool check_zero = (s_zero_union != 0);
+        const int Wn = (n + 31) >> 5;
+
+        for (int c = warp; c < C; c += NMS_WARPS) {
+            for (int e = lane; e < NPAD; e += 32) {
+                uint64_t k = ~0ull;
+                if (e < n) {
+                    const float s = __ldg(p.scores + (int64_t)srow[e] * p.score_ldr + (int64_t)c * p.score_ldc);
+                    k = ((uint64_t)f32_key_desc(s) << 32) | (uint32_t)e;
+                }
+                keys[e] = k;
+            }
+            __syncwarp();
+            for (int size = 2; size <= NPAD; size <<= 1) {
+                for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                    for (int t = lane; t < (NPAD >> 1); t += 32) {
+                        const int i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+                        const int j = i + stride;
+                        const uint64_t a = keys[i], b = keys[j];
+                        const bool up = (i & size) == 0;
+                        if (up ? (a > b) : (a < b)) { keys[i] = b; keys[j] = a; }
+                    }
+                    __syncwarp();
+                }
+            }
+            uint32_t rem0 = 0, rem1 = 0, kept0 = 0, kept1 = 0;
+            int cnt = 0;
+            int32_t buf = -1;
+            int32_t* out_idx = p.keep_idx + (int64_t)c * p.n_rows + off;
+            for (int k = 0; k < n; ++k) {
+                const uint32_t i = (uint32_t)keys[k];                       // broadcast read
+                const uint32_t w = i >> 5;
+                const uint32_t word = __shfl_sync(FULL, (w & 32) ? rem1 : rem0, (int)(w & 31));
+                if ((word >> (i & 31)) & 1u) continue;                      // warp-uniform
+                if (check_zero) {
+                    const float4 bi = sbox[i];
+                    const float ai = sarea[i];
+                    bool zd = false;
+                    for (int base = k + 1; base < n; base += 32) {            // warp-uniform trip count
+                        const int k2 = base + lane;
+                        const bool act = k2 < n;
+                        const uint32_t j = act ? (uint32_t)keys[k2] : 0u;
+                        // every lane needs the removed word of its own j: fetch both halves
+                        const uint32_t w0 = __shfl_sync(FULL, rem0, (int)((j >> 5) & 31));
+                        const uint32_t w1 = __shfl_sync(FULL, rem1, (int)((j >> 5) & 31));
+                        const uint32_t wj = ((j >> 5) & 32) ? w1 : w0;
+                        if (act && !((wj >> (j & 31)) & 1u)) {
+                            float inter, uni;
+                            inter_union_f32(bi, ai, sbox[j], sarea[j], inter, uni);
+                            zd |= (uni == 0.0f);
+                        }
+                    }
+                    if (__any_sync(FULL, zd) && lane == 0) atomicOr(p.status, VDET_STATUS_ZERO_DIVISION);
+                }
+                const uint32_t* row = gmask + (size_t)i * W;
+                if (lane < Wn) rem0 |= row[lane];
+                if (32 + lane < Wn) rem1 |= row[32 + lane];
+                if (lane == (int)(w & 31)) { if (w & 32) kept1 |= (1u << (i & 31)); else kept0 |= (1u << (i & 31)); }
+                if (lane == (cnt & 31)) buf = srow[i];
+                ++cnt;
+                if ((cnt & 31) == 0) out_idx[cnt - 32 + lane] = buf;
+            }
+            {
+                const int done = cnt & ~31;
+                if (done + lane < cnt) out_idx[done + lane] = buf;
+                for (int e = cnt + lane; e < n; e += 32) out_idx[e] = -1;
+                if (lane == 0) p.keep_cnt[(int64_t)c * p.n_segs + seg] = cnt;
+            }
+            if (p.keep_mask) {
+                uint8_t* out_m = p.keep_mask + (int64_t)c * p.n_rows + off;
+                for (int wi = 0; wi < Wn; ++wi) {
+                    const uint32_t kw = __shfl_sync(FULL, (wi & 32) ? kept1 : kept0, wi & 31);
+                    const int e = wi * 32 + lane;
+                    if (e < n) out_m[e] = (uint8_t)((kw >> lane) & 1u);
+                }
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+}
+
+static size_t big_smem_bytes(int nb, int npad) {
+    return (size_t)nb * (sizeof(float4) + sizeof(float) + sizeof(int32_t)) + (size_t)NMS_WARPS * npad * sizeof(uint64_t);
+}
+
 }  // namespace vdet
 
 using namespace vdet;
 
 extern "C" size_t vdet_nms_frames_workspace_bytes(int max_seg_len, int n_classes, int device) {
-    (void)max_seg_len; (void)n_classes; (void)device;
-    return 256;   // the register-sort variants keep everything in shared memory
+    (void)n_classes; (void)device;
+    if (max_seg_len <= 1024) return 256;   // register-sort variants keep everything in shared memory
+    const size_t nb = ((size_t)max_seg_len + 255) / 256 * 256;
+    return (size_t)sm_count_cached() * nb * (nb / 32) * sizeof(uint32_t) + 256;
 }
 
 extern "C" int vdet_nms_frames_f32(const float* boxes, int box_ld,
@@ -242,7 +450,6 @@ extern "C" int vdet_nms_frames_f32(const float* boxes, int box_ld,
                                    int32_t* keep_idx, int32_t* keep_cnt, uint8_t* keep_mask,
                                    int64_t n_rows, uint32_t* status,
                                    void* ws, size_t ws_bytes, void* stream) {
-    (void)ws; (void)ws_bytes;
     VDET_REQUIRE(n_segs >= 0 && n_classes >= 1 && n_rows >= 0 && max_seg_len >= 0, "nms_frames: negative size");
     VDET_REQUIRE(box_ld >= 4, "nms_frames: box_ld must be >= 4");
     VDET_REQUIRE(status != nullptr && keep_idx != nullptr && keep_cnt != nullptr, "nms_frames: null output");
@@ -251,11 +458,12 @@ extern "C" int vdet_nms_frames_f32(const float* boxes, int box_ld,
             VDET_CUDA(cudaMemsetAsync(keep_cnt, 0, sizeof(int32_t) * (size_t)n_segs * n_classes, (cudaStream_t)stream));
         return VDET_OK;
     }
-    if (max_seg_len > 1024) {
-        set_error("nms_frames: max_seg_len %d > 1024 is not supported by this build", max_seg_len);
+    if (max_seg_len > BIG_MAX) {
+        set_error("nms_frames: max_seg_len %d > %d is not supported by this build", max_seg_len, BIG_MAX);
         return VDET_ERR_UNSUPPORTED;
     }
     NmsFramesParams p;
+    p.gmask = nullptr; p.npad = 0;
     p.boxes = boxes; p.box_ld = box_ld;
     p.box_vec = (box_ld == 4) && ((reinterpret_cast<uintptr_t>(boxes) & 15) == 0);
     p.scores = scores; p.score_ldr = score_ldr; p.score_ldc = score_ldc;
@@ -264,15 +472,38 @@ extern "C" int vdet_nms_frames_f32(const float* boxes, int box_ld,
     p.thresh_f32 = thresh_ceil_f32(thresh);
     p.keep_idx = keep_idx; p.keep_cnt = keep_cnt; p.keep_mask = keep_mask;
     p.n_rows = n_rows; p.status = status;
+    if (max_seg_len > 1024) {
+        const int nb = (max_seg_len + 255) / 256 * 256;
+        p.nb = nb;
+        p.npad = BIG_MAX;
+        p.stage = 0;
+        int grid = sm_count_cached();
+        if (grid > n_segs) grid = n_segs;
+        const size_t need = (size_t)grid * nb * (nb / 32) * sizeof(uint32_t);
+        if (ws == nullptr || ws_bytes < need) {
+            set_error("nms_frames: workspace of %zu bytes needed for %d-box frames", need, max_seg_len);
+            return VDET_ERR_WORKSPACE;
+        }
+        p.gmask = (uint32_t*)ws;
+        const size_t smem = big_smem_bytes(nb, p.npad);
+        if (smem > max_dynamic_smem(nms_frames_big_kernel)) {
+            set_error("nms_frames: %zu bytes of shared memory needed", smem);
+            return VDET_ERR_UNSUPPORTED;
+        }
+        VDET_CUDA(allow_dynamic_smem(nms_frames_big_kernel, smem));
+        nms_frames_big_kernel<<<grid, NMS_THREADS, smem, (cudaStream_t)stream>>>(p);
+        VDET_LAUNCH_CHECK();
+        return VDET_OK;
+    }
     const int nb = max_seg_len <= 32 ? 32 : (max_seg_len + 31) / 32 * 32;   // shared-memory capacity
     p.nb = nb;
     int nper = 1;                                                           // sort network: 32*nper >= nb
     while (32 * nper < nb) nper <<= 1;
     // Stage scores when the block is box-major and the CTA still fits >= 2 per SM.
     const bool want_stage = (score_ldr != 1);
-    const size_t smem_stage = nms_smem_bytes(nb, n_classes, true);
+    const size_t smem_stage = nms_smem_bytes(nb, nper, n_classes, true);
     p.stage = (want_stage && smem_stage <= 100 * 1024) ? 1 : 0;
-    const size_t smem = nms_smem_bytes(nb, n_classes, p.stage != 0);
+    const size_t smem = nms_smem_bytes(nb, nper, n_classes, p.stage != 0);
     int per_sm = (int)((size_t)(220 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;

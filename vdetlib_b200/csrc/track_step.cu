@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(128) track_nms_step_kernel(const float* __rest
                 float inter, uni;
                 inter_union_f32(b, area_f32(b), tb, ta, inter, uni);
                 if (uni == 0.0f) zd = true;
-                else if (!(__fdiv_rn(inter, uni) >= T)) mine |= (1u << c);
+                else if (!iou_ge(inter, uni, T)) mine |= (1u << c);
             }
         }
     }
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(128) track_nms_step_kernel(const float* __rest
                 float inter, uni;
                 inter_union_f32(bi, ai, bj, area_f32(bj), inter, uni);
                 if (uni == 0.0f) zd = true;
-                else if (__fdiv_rn(inter, uni) >= T) mine &= ~(1u << c);
+                else if (iou_ge(inter, uni, T)) mine &= ~(1u << c);
             }
         }
     }

@@ -119,9 +119,81 @@ __global__ void k_track_round1(const float* __restrict__ tracks, int64_t q, int 
         float inter, uni;
         inter_union_f32(bi, ai, bj, area_f32(bj), inter, uni);
         if (uni == 0.0f) { atomicOr(status, VDET_STATUS_ZERO_DIVISION); break; }
-        if (__fdiv_rn(inter, uni) >= T) { sup = true; break; }
+        if (iou_ge(inter, uni, T)) { sup = true; break; }
     }
     valid[i] = sup ? 0 : 1;
+}
+
+
+__global__ void k_score_keys(const float* __restrict__ scores, int ld, int64_t n, uint32_t* __restrict__ keys,
+                             uint32_t* __restrict__ vals) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    keys[p] = f32_key_desc(__ldg(scores + p * (int64_t)ld));
+    vals[p] = (uint32_t)p;
+}
+
+// frame keys of rows taken in the order `vals` (already sorted by score)
+__global__ void k_frame_keys_perm(const float* __restrict__ frames, int ld, int64_t n,
+                                  const uint8_t* __restrict__ row_valid, const uint32_t* __restrict__ vals,
+                                  uint32_t* __restrict__ keys, SegCounters* cnt) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0) { cnt->n_packed = (int32_t)n; cnt->n_segs = 0; cnt->max_len = 0; }
+    if (p >= n) return;
+    const uint32_t r = vals[p];
+    const bool valid = row_valid ? (row_valid[r] != 0) : true;
+    keys[p] = valid ? f32_key_asc(__ldg(frames + (int64_t)r * ld)) : KEY_SENTINEL;
+}
+
+__global__ void k_gather_boxes(const float* __restrict__ boxes, int ld, const int32_t* __restrict__ row_ids,
+                               int64_t n, float4* __restrict__ out_box, float* __restrict__ out_area) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const float* b = boxes + (int64_t)row_ids[p] * ld;
+    const float4 v = make_float4(__ldg(b), __ldg(b + 1), __ldg(b + 2), __ldg(b + 3));
+    out_box[p] = v;
+    out_area[p] = area_f32(v);
+}
+
+// Any-length frames (more boxes than the bit-matrix kernels hold): one CTA per frame walks the
+// frame's boxes in descending score exactly like nms.pyx:43-66 -- a kept box i is tested on
+// the fly against every later box that is still alive (the CTA's threads stride over them),
+// so the pairs evaluated are precisely the pairs the reference visits, no bit matrix is stored
+// and the removed set (n bits) lives in shared memory.
+constexpr int OTF_THREADS = 512;
+
+__global__ void __launch_bounds__(OTF_THREADS) nms_segment_otf_kernel(const float4* __restrict__ sbox,
+                                                                      const float* __restrict__ sarea,
+                                                                      const int32_t* __restrict__ row_ids,
+                                                                      const int32_t* __restrict__ seg_offsets,
+                                                                      float T, int32_t* __restrict__ keep_idx,
+                                                                      int32_t* __restrict__ keep_cnt,
+                                                                      uint32_t* status) {
+    extern __shared__ uint32_t s_removed[];
+    const int seg = blockIdx.x;
+    const int off = seg_offsets[seg];
+    const int n = seg_offsets[seg + 1] - off;
+    const int tid = threadIdx.x;
+    for (int w = tid; w < (n + 31) / 32; w += OTF_THREADS) s_removed[w] = 0;
+    __syncthreads();
+    int cnt = 0;
+    for (int k = 0; k < n; ++k) {
+        if ((s_removed[k >> 5] >> (k & 31)) & 1u) continue;            // uniform across the CTA
+        if (tid == 0) keep_idx[off + cnt] = row_ids[off + k];
+        ++cnt;
+        const float4 bi = sbox[off + k];
+        const float ai = sarea[off + k];
+        for (int q = k + 1 + tid; q < n; q += OTF_THREADS) {
+            if ((s_removed[q >> 5] >> (q & 31)) & 1u) continue;
+            float inter, uni;
+            inter_union_f32(bi, ai, sbox[off + q], sarea[off + q], inter, uni);
+            if (uni == 0.0f) atomicOr(status, VDET_STATUS_ZERO_DIVISION);
+            else if (iou_ge(inter, uni, T)) atomicOr(&s_removed[q >> 5], 1u << (q & 31));
+        }
+        __syncthreads();
+    }
+    for (int e = cnt + tid; e < n; e += OTF_THREADS) keep_idx[off + e] = -1;
+    if (tid == 0) keep_cnt[seg] = cnt;
 }
 
 static inline unsigned blocks_for(int64_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
@@ -149,10 +221,22 @@ static size_t seg_ws_bytes(int64_t n) {
 }
 
 // Asynchronous part of vdet_segment_by_frame; counters stay on the device in w.cnt.
+// With `scores` != nullptr the rows are first put in descending-score order (stable), so that
+// after the stable sort by frame every segment is internally in descending score with ties
+// by ascending row -- the order the any-length path walks.
 static int segment_async(const float* frames, int ld, int64_t n, const uint8_t* row_valid,
                          int32_t* row_ids_out, int32_t* seg_offsets_out, float* seg_frame_out,
-                         SegWs& w, cudaStream_t st) {
-    k_frame_keys<<<blocks_for(n), 256, 0, st>>>(frames, ld, n, row_valid, w.keys, (uint32_t*)row_ids_out, w.cnt);
+                         SegWs& w, cudaStream_t st, const float* scores = nullptr, int sld = 0) {
+    if (scores != nullptr) {
+        k_score_keys<<<blocks_for(n), 256, 0, st>>>(scores, sld, n, w.keys, (uint32_t*)row_ids_out);
+        VDET_LAUNCH_CHECK();
+        int f0 = radix_sort_pairs(w.keys, (uint32_t*)row_ids_out, w.keys_alt, w.vals_alt, n, 0, 32, w.radix, st);
+        if (f0 != 0) { if (f0 > 0) set_error("segment: unexpected sort parity"); return f0 < 0 ? f0 : VDET_ERR_INVALID; }
+        k_frame_keys_perm<<<blocks_for(n), 256, 0, st>>>(frames, ld, n, row_valid, (const uint32_t*)row_ids_out,
+                                                         w.keys, w.cnt);
+    } else {
+        k_frame_keys<<<blocks_for(n), 256, 0, st>>>(frames, ld, n, row_valid, w.keys, (uint32_t*)row_ids_out, w.cnt);
+    }
     VDET_LAUNCH_CHECK();
     int flip = radix_sort_pairs(w.keys, (uint32_t*)row_ids_out, w.keys_alt, w.vals_alt, n, 0, 32, w.radix, st);
     if (flip < 0) return flip;
@@ -204,8 +288,11 @@ extern "C" size_t vdet_nms_workspace_bytes(int64_t n, int device) {
     (void)device;
     if (n < 1) n = 1;
     // segmenting + row_ids/seg_offsets/keep_idx/keep_cnt/flag/pos/k2/v2/k2a/v2a + valid + status
-    return seg_ws_bytes(n) + 10 * (size_t)(n + 2) * 4 + (size_t)n + radix_scratch_elems(n) * 4 +
-           scan_scratch_elems(n) * 4 + 32 * 256;
+    size_t b = seg_ws_bytes(n) + 10 * (size_t)(n + 2) * 4 + (size_t)n + radix_scratch_elems(n) * 4 +
+               scan_scratch_elems(n) * 4 + 40 * 256;
+    b += (size_t)(n + 2) * 20;                                   // gathered boxes + areas (any-length path)
+    if (n > 1024) b += vdet_nms_frames_workspace_bytes((int)(n < 2048 ? n : 2048), 1, device);
+    return b;
 }
 
 namespace {
@@ -251,10 +338,40 @@ int64_t nms_core(const float* dets, int64_t n, int ld, const float* frames, int 
     }
     if (n_packed == 0 || n_segs == 0) { *status_host = 0; return 0; }
 
-    int rc = vdet_nms_frames_f32(dets + box_col, ld, dets + score_col, ld, 0, seg_offsets, n_segs, max_len,
+    int rc;
+    if (max_len <= 2048) {
+        void* fws = nullptr;
+        size_t fws_bytes = 0;
+        if (max_len > 1024) {
+            fws_bytes = vdet_nms_frames_workspace_bytes(max_len, 1, 0);
+            fws = c.take<char>(fws_bytes);
+            if (!c.ok()) { set_error("nms: workspace too small"); return VDET_ERR_WORKSPACE; }
+        }
+        rc = vdet_nms_frames_f32(dets + box_col, ld, dets + score_col, ld, 0, seg_offsets, n_segs, max_len,
                                  row_ids_arg, 1, thresh, keep_idx, keep_cnt, nullptr, n_packed, status,
-                                 nullptr, 0, st);
-    if (rc != VDET_OK) return rc;
+                                 fws, fws_bytes, st);
+        if (rc != VDET_OK) return rc;
+    } else {
+        // any-length path: order every frame by descending score, gather, walk on the fly
+        float4* gbox = c.take<float4>(n + 1);
+        float* garea = c.take<float>(n + 1);
+        if (!c.ok()) { set_error("nms: workspace too small"); return VDET_ERR_WORKSPACE; }
+        const float* fr = frames ? frames : dets;
+        const int fld = frames ? ld : 0;
+        rc = segment_async(fr, fld, n, row_valid, row_ids, seg_offsets, nullptr, w, st, dets + score_col, ld);
+        if (rc != VDET_OK) return rc;
+        k_gather_boxes<<<blocks_for(n_packed), 256, 0, st>>>(dets + box_col, ld, row_ids, n_packed, gbox, garea);
+        VDET_LAUNCH_CHECK();
+        const size_t smem = ((size_t)max_len + 31) / 32 * sizeof(uint32_t);
+        if (smem > max_dynamic_smem(nms_segment_otf_kernel)) {
+            set_error("nms: a frame with %d boxes exceeds what this build handles", max_len);
+            return VDET_ERR_UNSUPPORTED;
+        }
+        VDET_CUDA(allow_dynamic_smem(nms_segment_otf_kernel, smem));
+        nms_segment_otf_kernel<<<n_segs, OTF_THREADS, smem, st>>>(gbox, garea, row_ids, seg_offsets,
+                                                                  thresh_ceil_f32(thresh), keep_idx, keep_cnt, status);
+        VDET_LAUNCH_CHECK();
+    }
 
     uint32_t h_total = 0, h_status = 0;
     if (n_segs == 1) {

@@ -19,9 +19,9 @@ __device__ __forceinline__ void warp_bitonic_sort(uint64_t (&k)[NPER], const int
                     const int q = lane * NPER + r;
                     const bool up = (q & size) == 0;
                     const uint64_t other = __shfl_xor_sync(FULL, k[r], lstride);
-                    const uint64_t mn = k[r] < other ? k[r] : other;
-                    const uint64_t mx = k[r] < other ? other : k[r];
-                    k[r] = (up == lower) ? mn : mx;
+                    // keys are distinct (the index is part of the key), so "other > k" == !(other < k)
+                    const bool lt = other < k[r];
+                    k[r] = (lt == (up == lower)) ? other : k[r];
                 }
             } else {
 #pragma unroll
@@ -31,7 +31,7 @@ __device__ __forceinline__ void warp_bitonic_sort(uint64_t (&k)[NPER], const int
                         const int q = lane * NPER + r;
                         const bool up = (q & size) == 0;
                         const uint64_t a = k[r], b = k[r2];
-                        const bool sw = up ? (a > b) : (a < b);
+                        const bool sw = ((a > b) == up);
                         k[r] = sw ? b : a;
                         k[r2] = sw ? a : b;
                     }

@@ -97,10 +97,14 @@ def nms_frames(boxes, scores, seg_offsets, thresh, max_seg_len, row_ids=None, wa
         status = new_status(dev)
     if row_ids is not None:
         _need(row_ids, "row_ids", torch.int32, 1)
+    ws, ws_bytes = None, 0
+    if max_seg_len > 1024:          # big frames keep their bit matrix in a global scratch slot per CTA
+        ws_bytes = lib.vdet_nms_frames_workspace_bytes(int(max_seg_len), C, dev.index or 0)
+        ws = _workspace(ws_bytes, dev)
     rc = lib.vdet_nms_frames_f32(_ptr(boxes), 4, _ptr(scores), ldr, ldc, _ptr(seg_offsets), S,
                                  int(max_seg_len), _ptr(row_ids), C, float(thresh),
                                  _ptr(keep_idx), _ptr(keep_cnt), _ptr(keep_mask), n, _ptr(status),
-                                 None, 0, _stream())
+                                 _ptr(ws), ws_bytes, _stream())
     _lib.check(rc, "nms_frames")
     return keep_idx, keep_cnt, keep_mask, status
 
