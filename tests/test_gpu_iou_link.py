@@ -109,3 +109,58 @@ def test_link_ragged_and_halo():
     hs, hb = c_oracle.link_f32(two, np.asarray([counts[-1], 50], np.int32))
     assert np.array_equal(succ.cpu().numpy()[n_linked:], hs[0, :counts[-1]])
     assert np.array_equal(best.cpu().numpy()[n_linked:], hb[0, :counts[-1]])
+
+
+def _weird_boxes(n, seed):
+    """Boxes that are NOT 'sane' for the branch-free division: huge coordinates, zero-area and
+    inverted boxes (negative areas, zero unions) mixed into ordinary ones."""
+    rng = np.random.default_rng(seed)
+    b = helpers.unique_score_dets(rng, n, scale=400.0)[:, :4]
+    b[::7] *= 2.0e4                                   # coordinates beyond 2^20
+    b[3::11, 2] = b[3::11, 0] - 1.0                   # width exactly 0  -> area 0
+    b[5::13, 2] = b[5::13, 0] - 30.0                  # inverted         -> negative width
+    b[6::17] = b[6::17][:, [0, 1, 0, 1]] - np.asarray([0, 0, 1, 1], np.float32)   # 0 x 0 boxes
+    return np.ascontiguousarray(b, np.float32)
+
+
+def test_iou_link_generic_path_on_weird_boxes():
+    a, b = _weird_boxes(150, 1), _weird_boxes(1100, 2)
+    got = ops.iou_matrix(torch.from_numpy(a).to(DEV), torch.from_numpy(b).to(DEV)).cpu().numpy()
+    want = c_oracle.pair_iou_f32(a, b)
+    assert np.array_equal(got, want, equal_nan=True)
+    assert np.isnan(want).any() or np.isinf(want).any() or (want < 0).any()       # the case is really exercised
+    a64, b64 = a.astype(np.float64), b.astype(np.float64)
+    with np.errstate(all="ignore"):
+        want64 = oracle_np.iou(a64, b64)
+    got64 = ops.iou_matrix(torch.from_numpy(a64).to(DEV), torch.from_numpy(b64).to(DEV)).cpu().numpy()
+    assert np.array_equal(got64, want64, equal_nan=True)
+    # link over frames of weird boxes
+    T, N = 4, 300
+    fr = np.stack([_weird_boxes(N, 10 + t) for t in range(T)])
+    want_s, want_b, off = _link_oracle_packed(fr, np.full(T, N, np.int32))
+    succ, best = ops.link_frames(torch.from_numpy(fr.reshape(-1, 4)).to(DEV),
+                                 ops.seg_offsets_uniform(T, N, torch.device(DEV)), N)
+    assert np.array_equal(succ.cpu().numpy()[:(T - 1) * N], want_s)
+    assert np.array_equal(best.cpu().numpy()[:(T - 1) * N], want_b, equal_nan=True)
+
+
+def test_nms_generic_path_on_weird_boxes():
+    """Thresholds outside the fast-filter range and boxes outside the sane range still match."""
+    from vdetlib_b200.utils import cython_nms as gpu
+    rng = np.random.default_rng(3)
+    for thr in (0.0, 1e-8, 0.3, 0.999999, 1.0, 1.5, 3.0, -0.5):
+        d = helpers.unique_score_dets(rng, 400)
+        assert gpu.nms(d, thr) == c_oracle.nms(d, thr), thr
+    d = helpers.unique_score_dets(rng, 500)
+    d[::7, :4] *= 2.0e4
+    d[5::13, 2] = d[5::13, 0] - 30.0          # inverted boxes: negative areas, unions can be <= 0
+    for thr in (0.3, 0.5):
+        try:
+            want = c_oracle.nms(d, thr)
+        except ZeroDivisionError:
+            want = None
+        if want is None:
+            with pytest.raises(ZeroDivisionError):
+                gpu.nms(d, thr)
+        else:
+            assert gpu.nms(d, thr) == want

@@ -20,8 +20,8 @@ constexpr int IOU_THREADS = 256;
 constexpr int IOU_TILE_C = IOU_THREADS * 4;   // 1024 columns per CTA
 constexpr int IOU_TILE_R = 32;                // rows per CTA
 
-template <bool VEC>
-__global__ void __launch_bounds__(IOU_THREADS) iou_matrix_f32_kernel(const float4* __restrict__ a, int64_t na,
+template <bool VEC, bool FAST>
+__device__ __forceinline__ void iou_matrix_f32_body(const float4* __restrict__ a, int64_t na,
                                                                      const float4* __restrict__ b, int64_t nb,
                                                                      float* __restrict__ out) {
     __shared__ float4 s_a[IOU_TILE_R];
@@ -29,13 +29,7 @@ __global__ void __launch_bounds__(IOU_THREADS) iou_matrix_f32_kernel(const float
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t c0 = (int64_t)blockIdx.x * IOU_TILE_C;
     const int64_t r0 = (int64_t)blockIdx.y * IOU_TILE_R;
-    if (tid < IOU_TILE_R) {
-        const int64_t r = r0 + tid;
-        const float4 v = r < na ? __ldg(a + r) : make_float4(0.f, 0.f, 0.f, 0.f);
-        s_a[tid] = v;
-        s_aa[tid] = area_f32(v);
-    }
-    // this thread's 4 columns
+    // this thread's 4 columns (re-read here: cheap, L1-resident after the sanity pass)
     int64_t col[4];
     float4 bb[4];
     float ba[4];
@@ -45,6 +39,12 @@ __global__ void __launch_bounds__(IOU_THREADS) iou_matrix_f32_kernel(const float
         bb[k] = col[k] < nb ? __ldg(b + col[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
         ba[k] = area_f32(bb[k]);
     }
+    if (tid < IOU_TILE_R) {
+        const int64_t r = r0 + tid;
+        const float4 v = r < na ? __ldg(a + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+        s_a[tid] = v;
+        s_aa[tid] = area_f32(v);
+    }
     __syncthreads();
     const int rows = (int)((na - r0) < IOU_TILE_R ? (na - r0) : IOU_TILE_R);
 #pragma unroll 2
@@ -53,7 +53,15 @@ __global__ void __launch_bounds__(IOU_THREADS) iou_matrix_f32_kernel(const float
         const float aa = s_aa[r];
         float v[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = pair_iou_f32(av, aa, bb[k], ba[k]);
+        for (int k = 0; k < 4; ++k) {
+            if (FAST) {
+                float inter, uni;
+                inter_union_f32(av, aa, bb[k], ba[k], inter, uni);
+                v[k] = div_sane(inter, uni);
+            } else {
+                v[k] = pair_iou_f32(av, aa, bb[k], ba[k]);
+            }
+        }
         float* row = out + (r0 + r) * nb;
         if (VEC) {
             if (col[3] < nb) {
@@ -69,6 +77,26 @@ __global__ void __launch_bounds__(IOU_THREADS) iou_matrix_f32_kernel(const float
                 if (col[k] < nb) __stcs(row + col[k], v[k]);
         }
     }
+}
+
+// The CTA first votes whether every box it touches is "sane" (common.cuh): if so the whole tile
+// uses the branch-free 6-instruction division, else the generic IEEE path.  Same bits either way.
+template <bool VEC>
+__global__ void __launch_bounds__(IOU_THREADS) iou_matrix_f32_kernel(const float4* __restrict__ a, int64_t na,
+                                                                     const float4* __restrict__ b, int64_t nb,
+                                                                     float* __restrict__ out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t c0 = (int64_t)blockIdx.x * IOU_TILE_C;
+    const int64_t r0 = (int64_t)blockIdx.y * IOU_TILE_R;
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t col = VEC ? (c0 + 4 * tid + k) : (c0 + warp * 128 + k * 32 + lane);
+        if (col < nb) ok = ok && box_sane(__ldg(b + col));
+    }
+    if (tid < IOU_TILE_R && r0 + tid < na) ok = ok && box_sane(__ldg(a + r0 + tid));
+    if (__syncthreads_and(ok)) iou_matrix_f32_body<VEC, true>(a, na, b, nb, out);
+    else iou_matrix_f32_body<VEC, false>(a, na, b, nb, out);
 }
 
 // utils/common.py:451-468 in float64, operation for operation.

@@ -39,22 +39,36 @@ __global__ void __launch_bounds__(LINK_THREADS) link_frames_kernel(const float4*
     const float ai = area_f32(bi);
     float best = -1.0f;        // every valid IoU is >= 0, so the first valid j always wins
     int arg = -1;
+    const bool own_sane = box_sane(bi);          // inactive lanes hold the (sane) zero box
     for (int j0 = 0; j0 < m; j0 += LINK_STAGE) {
         const int cnt = (m - j0) < LINK_STAGE ? (m - j0) : LINK_STAGE;
         __syncthreads();
+        bool ok = own_sane;
         for (int e = threadIdx.x; e < cnt; e += LINK_THREADS) {
             const float4 b = __ldg(nxt + j0 + e);
             s_box[e] = b;
             s_area[e] = area_f32(b);
+            ok = ok && box_sane(b);
         }
-        __syncthreads();
+        // barrier + vote: when every box in play is sane (common.cuh) the branch-free division is
+        // exact and unions cannot be zero; otherwise the generic IEEE path runs.  Same bits.
+        if (__syncthreads_and(ok)) {
 #pragma unroll 4
-        for (int j = 0; j < cnt; ++j) {
-            float inter, uni;
-            inter_union_f32(bi, ai, s_box[j], s_area[j], inter, uni);
-            const float v = iou_quotient(inter, uni);
-            // NaN (0/0) and union==0 never win; strict '>' keeps the FIRST maximum
-            if (uni != 0.0f && v > best) { best = v; arg = j0 + j; }
+            for (int j = 0; j < cnt; ++j) {
+                float inter, uni;
+                inter_union_f32(bi, ai, s_box[j], s_area[j], inter, uni);
+                const float v = div_sane(inter, uni);
+                if (v > best) { best = v; arg = j0 + j; }      // strict '>' keeps the FIRST maximum
+            }
+        } else {
+#pragma unroll 2
+            for (int j = 0; j < cnt; ++j) {
+                float inter, uni;
+                inter_union_f32(bi, ai, s_box[j], s_area[j], inter, uni);
+                const float v = iou_quotient(inter, uni);
+                // NaN (0/0) and union==0 never win
+                if (uni != 0.0f && (arg < 0 || v > best)) { best = v; arg = j0 + j; }
+            }
         }
     }
     if (active) {

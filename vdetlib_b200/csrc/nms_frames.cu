@@ -37,7 +37,55 @@ struct NmsFramesParams {
     int stage;     // 1: scores transposed into shared memory
     uint32_t* gmask;   // big-frame variant: per-CTA bit-matrix slots in global memory
     int npad;          // big-frame variant: power-of-two sort length >= nb
+    int fast_filter;   // 1: division-free threshold filter allowed (2^-20 <= T <= 2)
 };
+
+// One 32x32 tile of the suppression bit matrix: lane = row i (box in registers), the 32 columns
+// of block `cb` are broadcast from shared memory.  Returns this lane's word for row i and, in
+// `tword`, the transposed word (row cb*32+lane, columns = this row block) collected from
+// ballots -- IoU is symmetric bit for bit (max/min/add commute), so only tiles with cb >= rb are
+// evaluated.
+//
+// FAST: the threshold test avoids the IEEE division.  fl(inter/uni) >= T holds iff
+// inter/uni >= m for a midpoint m in (T(1-2^-24), T]; with p = fl(T*uni) (relative error
+// <= 2^-24): inter > p(1+2^-21) proves the test true, inter < p(1-2^-21) proves it false.  Pairs
+// in between (or with uni <= 0 / NaN) set `uncertain`, and the caller redoes the tile with the
+// exact division (FAST = false).  Results are identical to the exact path by construction.
+// The host enables FAST only for 2^-20 <= T <= 2, and unions outside (1e-30, 1e30) are
+// "uncertain", so T*uni can neither overflow nor go subnormal.
+template <bool FAST>
+__device__ __forceinline__ uint32_t mask_tile(const float4 bi, const float ai, const float4* __restrict__ sbox,
+                                              const float* __restrict__ sarea, const int cb, const float T,
+                                              const int lane, uint32_t& tword, bool& zero, bool& uncertain) {
+    uint32_t word = 0, tw = 0;
+    bool z = false, unc = false;
+#pragma unroll 8
+    for (int jj = 0; jj < 32; ++jj) {
+        const int j = cb * 32 + jj;
+        const float4 bj = sbox[j];
+        const float aj = sarea[j];
+        float inter, uni;
+        inter_union_f32(bi, ai, bj, aj, inter, uni);
+        bool sup;
+        if (FAST) {
+            const float pth = __fmul_rn(T, uni);
+            const float hi = __fmaf_rn(pth, 4.76837158203125e-07f, pth);     // p * (1 + 2^-21)
+            const float lo = __fmaf_rn(pth, -4.76837158203125e-07f, pth);    // p * (1 - 2^-21)
+            sup = inter > hi;
+            unc |= !(sup || inter < lo) || !(uni > 1e-30f && uni < 1e30f);
+        } else {
+            sup = iou_ge(inter, uni, T);
+        }
+        z |= (uni == 0.0f);
+        if (sup) word |= (1u << jj);
+        const unsigned b = __ballot_sync(FULL, sup);
+        if (lane == jj) tw = b;
+    }
+    tword = tw;
+    zero = z;
+    uncertain = unc;
+    return word;
+}
 
 // Exact ZeroDivisionError test of nms.pyx:64 (cold path, only for frames that contain a
 // zero-union pair at all): the pair (ci, j) is visited by the reference iff j comes later in the
@@ -120,32 +168,35 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 2 : 1)) nms_frames_
                 }
             }
         }
-        // ---- B: suppression bit matrix, original index space ------------------------------
+        // ---- B: suppression bit matrix, original index space, upper-triangular tiles -------
         {
             const int Wn = (n + 31) >> 5;          // blocks actually populated by this frame
-            const int ntiles = Wn * Wn;
-            for (int tile = warp; tile < ntiles; tile += NMS_WARPS) {
-                const int rb = tile / Wn, cb = tile - rb * Wn;
-                const int i = rb * 32 + lane;
-                const float4 bi = sbox[i];
-                const float ai = sarea[i];
-                uint32_t word = 0;
-                bool zero = false;
-#pragma unroll 8
-                for (int jj = 0; jj < 32; ++jj) {
-                    const int j = cb * 32 + jj;
-                    const float4 bj = sbox[j];
-                    const float aj = sarea[j];
-                    float inter, uni;
-                    inter_union_f32(bi, ai, bj, aj, inter, uni);
-                    if (iou_ge(inter, uni, T)) word |= (1u << jj);
-                    zero |= (uni == 0.0f) && (i != j) && (i < n) && (j < n);
+            int t = 0;
+            for (int rb = 0; rb < Wn; ++rb) {
+                for (int cb = rb; cb < Wn; ++cb, ++t) {
+                    if ((t & (NMS_WARPS - 1)) != warp) continue;
+                    const int i = rb * 32 + lane;
+                    const float4 bi = sbox[i];
+                    const float ai = sarea[i];
+                    uint32_t tword;
+                    bool zero, unc;
+                    uint32_t word;
+                    if (p.fast_filter) {
+                        word = mask_tile<true>(bi, ai, sbox, sarea, cb, T, lane, tword, zero, unc);
+                        if (__any_sync(FULL, unc))   // a pair too close to the threshold: exact redo
+                            word = mask_tile<false>(bi, ai, sbox, sarea, cb, T, lane, tword, zero, unc);
+                    } else {
+                        word = mask_tile<false>(bi, ai, sbox, sarea, cb, T, lane, tword, zero, unc);
+                    }
+                    // columns / rows beyond the frame never suppress and are never visited
+                    const int cvalid = n - cb * 32, rvalid = n - rb * 32;
+                    if (cvalid < 32) word &= (1u << cvalid) - 1u;
+                    if (rvalid < 32) tword &= (1u << rvalid) - 1u;
+                    smask[i * WS + cb] = word;
+                    if (cb != rb) smask[(cb * 32 + lane) * WS + rb] = tword;
+                    // (a spurious flag from padding or the diagonal only enables the exact check)
+                    if (__any_sync(FULL, zero) && lane == 0) s_zero_union = 1;
                 }
-                // columns beyond the frame never suppress / are never visited
-                const int valid = n - cb * 32;
-                if (valid < 32) word &= (valid <= 0) ? 0u : ((1u << valid) - 1u);
-                smask[i * WS + cb] = word;
-                if (__any_sync(FULL, zero) && lane == 0) s_zero_union = 1;
             }
         }
         __syncthreads();
@@ -186,15 +237,13 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 2 : 1)) nms_frames_
             }
 
             uint32_t rem = 0;        // lane w: word w of the removed set
-            uint32_t kept = 0;       // lane w: word w of the kept set
-            int cnt = 0;
-            int32_t buf = -1;        // lane (cnt & 31) buffers the cnt-th kept row
-            int32_t* out_idx = p.keep_idx + (int64_t)c * p.n_rows + off;
+            uint32_t kg[NPER];       // kg[g] (warp-uniform): lanes of group g whose candidate is kept
             // Greedy walk, 32 candidates per step: every lane tests its own candidate against the
             // removed set, a ballot gives the alive ones; the lowest alive lane is by construction
             // the next kept box, its mask row is OR-ed in and kills later lanes of the same group.
 #pragma unroll
             for (int g = 0; g < NPER; ++g) {
+                kg[g] = 0;
                 if (g * 32 < n) {                                             // warp-uniform
                     const uint32_t i = ord[g];
                     const bool valid = (g * 32 + lane) < n;
@@ -208,30 +257,31 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 2 : 1)) nms_frames_
                                                 lane, p.status);
                         const uint32_t roww = (lane < Wn) ? smask[ci * WS + lane] : 0u;
                         rem |= roww;
-                        if (lane == (int)(ci >> 5)) kept |= (1u << (ci & 31));
-                        if (lane == (cnt & 31)) buf = srow[ci];
-                        ++cnt;
-                        if ((cnt & 31) == 0) out_idx[cnt - 32 + lane] = buf;
+                        kg[g] |= (1u << l);
                         const uint32_t wv = __shfl_sync(FULL, roww, (int)((i >> 5) & 31));
                         alive &= ~__ballot_sync(FULL, (wv >> (i & 31)) & 1u);
                         alive &= ~(1u << l);
                     }
                 }
             }
-            // flush the partial group, pad the frame's remaining slots with -1
+            // outputs: kept rows in walk (= descending score) order, -1 padding, count, byte mask
             {
-                const int done = cnt & ~31;
-                if (done + lane < cnt) out_idx[done + lane] = buf;
+                int32_t* out_idx = p.keep_idx + (int64_t)c * p.n_rows + off;
+                uint8_t* out_m = p.keep_mask ? p.keep_mask + (int64_t)c * p.n_rows + off : nullptr;
+                const unsigned lt = lanemask_lt();
+                int cnt = 0;
+#pragma unroll
+                for (int g = 0; g < NPER; ++g) {
+                    if (g * 32 < n) {
+                        const uint32_t i = ord[g];
+                        const bool mine = (kg[g] >> lane) & 1u;
+                        if (mine) out_idx[cnt + __popc(kg[g] & lt)] = srow[i];
+                        if (out_m && (g * 32 + lane) < n) out_m[i] = (uint8_t)mine;
+                        cnt += __popc(kg[g]);
+                    }
+                }
                 for (int e = cnt + lane; e < n; e += 32) out_idx[e] = -1;
                 if (lane == 0) p.keep_cnt[(int64_t)c * p.n_segs + seg] = cnt;
-            }
-            if (p.keep_mask) {
-                uint8_t* out_m = p.keep_mask + (int64_t)c * p.n_rows + off;
-                for (int wi = 0; wi < Wn; ++wi) {
-                    const uint32_t kw = __shfl_sync(FULL, kept, wi);
-                    const int e = wi * 32 + lane;
-                    if (e < n) out_m[e] = (uint8_t)((kw >> lane) & 1u);
-                }
             }
         }
         __syncthreads();   // smem is reused by the next frame
@@ -464,6 +514,10 @@ extern "C" int vdet_nms_frames_f32(const float* boxes, int box_ld,
     }
     NmsFramesParams p;
     p.gmask = nullptr; p.npad = 0;
+    {
+        const float Tf = thresh_ceil_f32(thresh);
+        p.fast_filter = (Tf >= 9.5367431640625e-07f && Tf <= 2.0f) ? 1 : 0;
+    }
     p.boxes = boxes; p.box_ld = box_ld;
     p.box_vec = (box_ld == 4) && ((reinterpret_cast<uintptr_t>(boxes) & 15) == 0);
     p.scores = scores; p.score_ldr = score_ldr; p.score_ldc = score_ldc;
