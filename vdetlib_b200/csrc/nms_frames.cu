@@ -38,6 +38,7 @@ struct NmsFramesParams {
     uint32_t* gmask;   // big-frame variant: per-CTA bit-matrix slots in global memory
     int npad;          // big-frame variant: power-of-two sort length >= nb
     int fast_filter;   // 1: division-free threshold filter allowed (2^-20 <= T <= 2)
+    int so_words;      // per-warp order scratch: (nb/32)*33 words
 };
 
 // One 32x32 tile of the suppression bit matrix: lane = row i (box in registers), the 32 columns
@@ -110,7 +111,7 @@ __device__ __noinline__ void zero_division_check(const uint32_t* so, int ngroups
 }
 
 template <int NPER>
-__global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 2 : 1)) nms_frames_kernel(const NmsFramesParams p) {
+__global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 3 : 1)) nms_frames_kernel(const NmsFramesParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NB = p.nb;
     const int W = NB >> 5;          // mask words per row (<= 32 in this variant)
@@ -120,8 +121,8 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 2 : 1)) nms_frames_
     float* sarea = reinterpret_cast<float*>(sbox + NB);
     int32_t* srow = reinterpret_cast<int32_t*>(sarea + NB);
     uint32_t* smask = reinterpret_cast<uint32_t*>(srow + NB);
-    uint32_t* sord = smask + (size_t)NB * WS;                       // [NMS_WARPS][NPER*33] walk-order scratch
-    float* sscore = reinterpret_cast<float*>(sord + NMS_WARPS * NPER * 33);
+    uint32_t* sord = smask + (size_t)NB * WS;                       // [NMS_WARPS][so_words] order scratch
+    float* sscore = reinterpret_cast<float*>(sord + NMS_WARPS * p.so_words);
     __shared__ int s_zero_union;
 
     const int tid = threadIdx.x;
@@ -203,86 +204,119 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 2 : 1)) nms_frames_
         const bool check_zero = (s_zero_union != 0);
         const int Wn = (n + 31) >> 5;
 
-        // ---- C: per class: sort + greedy walk (one warp per class) -----------------------
+        // ---- C: per class: order by score + greedy walk (one warp per class) ---------------
+        uint32_t* so = sord + warp * p.so_words;          // this warp's order scratch (skewed)
+        const int cap = Wn * 32;                          // sorted positions >= cap are padding
         for (int c = warp; c < C; c += NMS_WARPS) {
-            uint64_t key[NPER];
+            const float* sc_smem = sscore + c * SST;
+            const float* sc_glob = p.scores + (int64_t)c * p.score_ldc;
+            auto score_key = [&](const int e) -> uint32_t {
+                const float sv = p.stage ? sc_smem[e] : __ldg(sc_glob + (int64_t)srow[e] * p.score_ldr);
+                return f32_key_desc(sv);
+            };
+            // -- order: so[skew(pos)] = index of the pos-th highest score (ties: lower index first).
+            // Fast path: sort the 32-bit score keys alone, then every element finds its rank by
+            // binary search in the sorted keys.  Equal keys (tied scores) make ranks ambiguous, so
+            // a tie anywhere in the problem takes the 64-bit (key,index) network instead.
+            bool ordered = false;
+            {
+                uint32_t k32[NPER];
 #pragma unroll
-            for (int r = 0; r < NPER; ++r) {
-                const int e = r * 32 + lane;      // striped load: conflict-free / coalesced
-                key[r] = ~0ull;                   // padding sorts last
-                if (e < n) {
-                    const float s = p.stage
-                        ? sscore[c * SST + e]
-                        : __ldg(p.scores + (int64_t)srow[e] * p.score_ldr + (int64_t)c * p.score_ldc);
-                    key[r] = ((uint64_t)f32_key_desc(s) << 32) | (uint32_t)e;
+                for (int r = 0; r < NPER; ++r) {
+                    const int e = r * 32 + lane;              // striped: conflict-free / coalesced
+                    k32[r] = e < n ? score_key(e) : 0xffffffffu;
+                }
+                warp_bitonic_sort_u32<NPER>(k32, lane);       // blocked: position lane*NPER + r
+                bool tie = false;
+#pragma unroll
+                for (int r = 0; r + 1 < NPER; ++r) tie |= (k32[r] == k32[r + 1]) && (lane * NPER + r + 1 < n);
+                const uint32_t nxt = __shfl_down_sync(FULL, k32[0], 1);
+                tie |= (lane < 31) && (k32[NPER - 1] == nxt) && ((lane + 1) * NPER < n);
+                if (!__any_sync(FULL, tie)) {
+                    __syncwarp();
+#pragma unroll
+                    for (int r = 0; r < NPER; ++r) {
+                        const int pp = lane * NPER + r;
+                        if (pp < cap) so[pp + (pp >> 5)] = k32[r];
+                    }
+                    __syncwarp();
+                    uint32_t rank[NPER];
+#pragma unroll
+                    for (int r = 0; r < NPER; ++r) {
+                        const int e = r * 32 + lane;
+                        uint32_t pos = 0;
+                        if (e < n) {
+                            const uint32_t key = score_key(e);
+#pragma unroll
+                            for (int step = 16 * NPER; step > 0; step >>= 1) {
+                                const uint32_t q = pos + step - 1;
+                                if (q < (uint32_t)n && so[q + (q >> 5)] < key) pos += step;
+                            }
+                        }
+                        rank[r] = pos;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int r = 0; r < NPER; ++r) {
+                        const int e = r * 32 + lane;
+                        if (e < n) so[rank[r] + (rank[r] >> 5)] = (uint32_t)e;
+                    }
+                    ordered = true;
                 }
             }
-            warp_bitonic_sort<NPER>(key, lane);
-
-            // blocked (sort) -> striped (walk) layout of the sorted indices through this warp's
-            // shared scratch: ord[g] = index at sorted position g*32 + lane.  The +p/32 skew
-            // makes both the blocked writes and the striped reads conflict-free.
-            uint32_t ord[NPER];
-            {
-                uint32_t* so = sord + warp * (NPER * 33);
+            if (!ordered) {
+                uint64_t key[NPER];
+#pragma unroll
+                for (int r = 0; r < NPER; ++r) {
+                    const int e = r * 32 + lane;
+                    key[r] = e < n ? (((uint64_t)score_key(e) << 32) | (uint32_t)e) : ~0ull;
+                }
+                warp_bitonic_sort<NPER>(key, lane);
                 __syncwarp();
 #pragma unroll
                 for (int r = 0; r < NPER; ++r) {
                     const int pp = lane * NPER + r;
-                    so[pp + (pp >> 5)] = (uint32_t)key[r];
+                    if (pp < cap) so[pp + (pp >> 5)] = (uint32_t)key[r];
                 }
-                __syncwarp();
-#pragma unroll
-                for (int g = 0; g < NPER; ++g) ord[g] = so[g * 33 + lane];
             }
+            __syncwarp();
 
-            uint32_t rem = 0;        // lane w: word w of the removed set
-            uint32_t kg[NPER];       // kg[g] (warp-uniform): lanes of group g whose candidate is kept
-            // Greedy walk, 32 candidates per step: every lane tests its own candidate against the
+            // -- greedy walk, 32 candidates per step: every lane tests its own candidate against the
             // removed set, a ballot gives the alive ones; the lowest alive lane is by construction
             // the next kept box, its mask row is OR-ed in and kills later lanes of the same group.
-#pragma unroll
-            for (int g = 0; g < NPER; ++g) {
-                kg[g] = 0;
-                if (g * 32 < n) {                                             // warp-uniform
-                    const uint32_t i = ord[g];
-                    const bool valid = (g * 32 + lane) < n;
-                    const uint32_t w = __shfl_sync(FULL, rem, (int)((i >> 5) & 31));
-                    unsigned alive = __ballot_sync(FULL, valid && !((w >> (i & 31)) & 1u));
-                    while (alive) {
-                        const int l = __ffs(alive) - 1;
-                        const uint32_t ci = __shfl_sync(FULL, i, l);          // the kept box
-                        if (check_zero)
-                            zero_division_check(sord + warp * (NPER * 33), NPER, sbox, sarea, rem, ci, g * 32 + l, n,
-                                                lane, p.status);
-                        const uint32_t roww = (lane < Wn) ? smask[ci * WS + lane] : 0u;
-                        rem |= roww;
-                        kg[g] |= (1u << l);
-                        const uint32_t wv = __shfl_sync(FULL, roww, (int)((i >> 5) & 31));
-                        alive &= ~__ballot_sync(FULL, (wv >> (i & 31)) & 1u);
-                        alive &= ~(1u << l);
-                    }
+            uint32_t rem = 0;        // lane w: word w of the removed set
+            int cnt = 0;
+            int32_t* out_idx = p.keep_idx + (int64_t)c * p.n_rows + off;
+            uint8_t* out_m = p.keep_mask ? p.keep_mask + (int64_t)c * p.n_rows + off : nullptr;
+            const unsigned lt = lanemask_lt();
+#pragma unroll 1
+            for (int g = 0; g < Wn; ++g) {
+                const bool valid = (g * 32 + lane) < n;
+                const uint32_t i = valid ? so[g * 33 + lane] : 0u;
+                const uint32_t w = __shfl_sync(FULL, rem, (int)(i >> 5));
+                unsigned alive = __ballot_sync(FULL, valid && !((w >> (i & 31)) & 1u));
+                unsigned kgrp = 0;   // lanes of this group whose candidate is kept (warp-uniform)
+                while (alive) {
+                    const int l = __ffs(alive) - 1;
+                    const uint32_t ci = __shfl_sync(FULL, i, l);              // the kept box
+                    if (check_zero)
+                        zero_division_check(so, Wn, sbox, sarea, rem, ci, g * 32 + l, n, lane, p.status);
+                    const uint32_t roww = (lane < Wn) ? smask[ci * WS + lane] : 0u;
+                    rem |= roww;
+                    kgrp |= (1u << l);
+                    const uint32_t wv = __shfl_sync(FULL, roww, (int)(i >> 5));
+                    alive &= ~__ballot_sync(FULL, (wv >> (i & 31)) & 1u);
+                    alive &= ~(1u << l);
                 }
+                // outputs of this group: kept rows in walk (= descending score) order, byte mask
+                const bool mine = (kgrp >> lane) & 1u;
+                if (mine) out_idx[cnt + __popc(kgrp & lt)] = srow[i];
+                if (out_m && valid) out_m[i] = (uint8_t)mine;
+                cnt += __popc(kgrp);
             }
-            // outputs: kept rows in walk (= descending score) order, -1 padding, count, byte mask
-            {
-                int32_t* out_idx = p.keep_idx + (int64_t)c * p.n_rows + off;
-                uint8_t* out_m = p.keep_mask ? p.keep_mask + (int64_t)c * p.n_rows + off : nullptr;
-                const unsigned lt = lanemask_lt();
-                int cnt = 0;
-#pragma unroll
-                for (int g = 0; g < NPER; ++g) {
-                    if (g * 32 < n) {
-                        const uint32_t i = ord[g];
-                        const bool mine = (kg[g] >> lane) & 1u;
-                        if (mine) out_idx[cnt + __popc(kg[g] & lt)] = srow[i];
-                        if (out_m && (g * 32 + lane) < n) out_m[i] = (uint8_t)mine;
-                        cnt += __popc(kg[g]);
-                    }
-                }
-                for (int e = cnt + lane; e < n; e += 32) out_idx[e] = -1;
-                if (lane == 0) p.keep_cnt[(int64_t)c * p.n_segs + seg] = cnt;
-            }
+            for (int e = cnt + lane; e < n; e += 32) out_idx[e] = -1;
+            if (lane == 0) p.keep_cnt[(int64_t)c * p.n_segs + seg] = cnt;
+            __syncwarp();
         }
         __syncthreads();   // smem is reused by the next frame
     }
@@ -292,7 +326,7 @@ static size_t nms_smem_bytes(int nb, int nper, int n_classes, bool stage) {
     const int W = nb / 32, WS = W | 1;
     size_t b = (size_t)nb * (sizeof(float4) + sizeof(float) + sizeof(int32_t));
     b += (size_t)nb * WS * sizeof(uint32_t);
-    b += (size_t)NMS_WARPS * nper * 33 * sizeof(uint32_t);
+    b += (size_t)NMS_WARPS * (nb / 32) * 33 * sizeof(uint32_t);
     if (stage) b += (size_t)n_classes * (nb + 1) * sizeof(float);
     return b;
 }
@@ -551,6 +585,7 @@ extern "C" int vdet_nms_frames_f32(const float* boxes, int box_ld,
     }
     const int nb = max_seg_len <= 32 ? 32 : (max_seg_len + 31) / 32 * 32;   // shared-memory capacity
     p.nb = nb;
+    p.so_words = (nb / 32) * 33;
     int nper = 1;                                                           // sort network: 32*nper >= nb
     while (32 * nper < nb) nper <<= 1;
     // Stage scores when the block is box-major and the CTA still fits >= 2 per SM.
@@ -561,6 +596,7 @@ extern "C" int vdet_nms_frames_f32(const float* boxes, int box_ld,
     int per_sm = (int)((size_t)(220 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
+    if (nper > 16) per_sm = 1; else if (per_sm > 3) per_sm = 3;      // register-limited residency
     int grid = sm_count_cached() * per_sm;
     if (grid > n_segs) grid = n_segs;
     cudaStream_t st = (cudaStream_t)stream;

@@ -41,4 +41,39 @@ __device__ __forceinline__ void warp_bitonic_sort(uint64_t (&k)[NPER], const int
     }
 }
 
+// 32-bit keys only: a compare-exchange is one VIMNMX per output (min or max picked by a
+// predicate), against ~7 ALU instructions for the 64-bit (key,index) network above.
+template <int NPER>
+__device__ __forceinline__ void warp_bitonic_sort_u32(uint32_t (&k)[NPER], const int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32 * NPER; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= NPER) {
+                const int lstride = stride / NPER;
+                const bool lower = (lane & lstride) == 0;
+                const bool up = ((lane * NPER) & size) == 0;
+                const bool keep_min = (up == lower);
+#pragma unroll
+                for (int r = 0; r < NPER; ++r) {
+                    const uint32_t other = __shfl_xor_sync(FULL, k[r], lstride);
+                    k[r] = keep_min ? min(k[r], other) : max(k[r], other);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < NPER; ++r) {
+                    const int r2 = r ^ stride;
+                    if (r2 > r) {
+                        const int q = lane * NPER + r;
+                        const bool up = (q & size) == 0;
+                        const uint32_t a = k[r], b = k[r2];
+                        k[r] = up ? min(a, b) : max(a, b);
+                        k[r2] = up ? max(a, b) : min(a, b);
+                    }
+                }
+            }
+        }
+    }
+}
+
 }  // namespace vdet
