@@ -269,8 +269,18 @@ def run_b200(args):
     else:
         dom, dom_ms, dom_bytes = "link_frames_kernel", ms_link, bytes_link
     achieved = dom_bytes / (dom_ms / 1000.0) / 1e9
+    traffic = None            # dram read+write of that kernel from the committed ncu --set full capture
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu.json")))["kernels"]
+        for name, caps in prof.items():
+            if dom in name and caps[0].get("dram_read") is not None:
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                traffic = (caps[0]["dram_read"] * scale.get(caps[0]["dram_read_unit"], 1.0) +
+                           caps[0]["dram_write"] * scale.get(caps[0]["dram_write_unit"], 1.0))
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
                 "kernels_ms": {"nms_frames_kernel": ms_nms, "link_frames_kernel": ms_link},
                 "note": "the step's kernels are issue/latency bound (sort + greedy walk + N^2 pair IoUs per "

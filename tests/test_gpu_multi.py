@@ -1,0 +1,92 @@
+"""Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): the frame-sharded pipeline with the NCCL
+boundary all-gather equals the single-GPU result on the whole video.  Also a single-GPU
+"virtual shard" check that exercises the same halo logic with one device."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from vdetlib_b200 import ops, synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _full_reference(b, s, thr):
+    T, N, C = s.shape
+    dev = torch.device("cuda", 0)
+    db = torch.from_numpy(b.reshape(-1, 4)).to(dev)
+    ds = torch.from_numpy(s.reshape(-1, C)).to(dev)
+    seg = ops.seg_offsets_uniform(T, N, dev)
+    _, cnt, mask, st = ops.nms_frames(db, ds, seg, thr, N, want_mask=True)
+    succ, iou = ops.link_frames(db, seg, N)
+    ops.raise_for_status(st)
+    return cnt.cpu().numpy(), mask.cpu().numpy(), succ.cpu().numpy(), iou.cpu().numpy()
+
+
+def test_virtual_shards_single_gpu():
+    """S logical shards on one device: link of every shard with the next shard's first frame as halo."""
+    T, N, C, thr, S = 24, 100, 3, 0.3, 4
+    b, s = synth.boxes_scores(T, N, C, seed=12)
+    cnt, mask, succ, iou = _full_reference(b, s, thr)
+    dev = torch.device("cuda", 0)
+    per = T // S
+    for k in range(S):
+        sb = torch.from_numpy(b[k * per:(k + 1) * per].reshape(-1, 4)).to(dev)
+        seg = ops.seg_offsets_uniform(per, N, dev)
+        halo = torch.from_numpy(b[(k + 1) * per]).to(dev) if k < S - 1 else None
+        su, io = ops.link_frames(sb, seg, N, halo)
+        su = su.cpu().numpy().astype(np.int64)
+        want = succ[k * per * N:(k + 1) * per * N].astype(np.int64)
+        # inside the shard successors are shard-local rows; across the boundary they index the halo
+        local = np.where(want >= 0, want - k * per * N, -1)
+        local[(per - 1) * N:] = np.where(want[(per - 1) * N:] >= 0, want[(per - 1) * N:] - (k + 1) * per * N, -1)
+        assert np.array_equal(su, local)
+        assert np.array_equal(io.cpu().numpy(), iou[k * per * N:(k + 1) * per * N])
+
+
+def _worker(rank, world, port, T, N, C, thr, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from vdetlib_b200.dist import ShardedVideoPostProcessor, shard_range
+    b, s = synth.boxes_scores(T, N, C, seed=12)
+    a, e = shard_range(T, world, rank)
+    pp = ShardedVideoPostProcessor(e - a, N, C, thr, dev)
+    pp.pp.stage(b[a:e], s[a:e])
+    res = pp.step_host()
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), **{k: np.array(v) for k, v in res.items()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_pipeline_matches_single_gpu(tmp_path, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    import torch.multiprocessing as mp
+    T, N, C, thr = 8 * world, 300, 30, 0.3          # equal shards: every rank holds 8 frames
+    b, s = synth.boxes_scores(T, N, C, seed=12)
+    cnt, mask, succ, iou = _full_reference(b, s, thr)
+    sock = socket.socket(); sock.bind(("127.0.0.1", 0)); port = sock.getsockname()[1]; sock.close()
+    mp.spawn(_worker, args=(world, port, T, N, C, thr, str(tmp_path)), nprocs=world, join=True)
+    per = T // world
+    for r in range(world):
+        got = np.load(os.path.join(str(tmp_path), "rank%d.npz" % r))
+        lo, hi = r * per * N, (r + 1) * per * N
+        assert np.array_equal(got["keep_cnt"], cnt[:, r * per:(r + 1) * per])
+        assert np.array_equal(got["keep_mask"], mask[:, lo:hi])
+        assert np.array_equal(got["link_iou"], iou[lo:hi])
+        want = succ[lo:hi].astype(np.int64)
+        local = np.where(want >= 0, want - lo, -1)
+        if r < world - 1:
+            local[(per - 1) * N:] = np.where(want[(per - 1) * N:] >= 0, want[(per - 1) * N:] - hi, -1)
+        assert np.array_equal(got["succ"].astype(np.int64), local)
