@@ -197,6 +197,7 @@ def run_b200(args):
             return 2
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout = the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     T, N, C = T_FRAMES, N_BOXES, N_CLASSES
