@@ -52,6 +52,14 @@ extern "C" {
 #define VDET_PAD_ZERO 0
 #define VDET_PAD_EDGE 1
 
+/* Output layouts of vdet_nms_frames_f32 (n_s = boxes of frame s, o_s = seg_offsets[s]):
+ *   CLASS_MAJOR: keep_idx / keep_mask [C, n_rows]: (class c, frame s) block at c*n_rows + o_s;
+ *                keep_cnt [C, S].  One plane per class = what apply_vid_nms returns per class.
+ *   FRAME_MAJOR: (frame s, class c) block at o_s*C + c*n_s; keep_cnt [S, C].  A contiguous range
+ *                of frames is a contiguous range of every output (chunked / pipelined D2H). */
+#define VDET_LAYOUT_CLASS_MAJOR 0
+#define VDET_LAYOUT_FRAME_MAJOR 1
+
 int         vdet_abi_version(void);
 const char* vdet_last_error(void);
 /* Number of SMs of `device` (grid sizing for callers); <0 on error. */
@@ -71,14 +79,14 @@ int         vdet_sm_count(int device);
  *                Boxes/scores are read at row_ids[p]; outputs report row_ids[p].
  *   thresh       IoU threshold as the reference's Python float (double); suppression test
  *                is (double)iou_f32 >= thresh  (nms.pyx:65)
- *   keep_idx     [C, n_rows] int32: for class c and frame s, entries
- *                [seg_offsets[s], seg_offsets[s]+keep_cnt[c*S+s]) are the kept rows in
- *                descending score (ties: ascending row); the rest of the frame's slots = -1
- *   keep_cnt     [C, S] int32
- *   keep_mask    optional [C, n_rows] uint8 (1 = kept), indexed by PACKED row p
+ *   keep_idx     int32, C*n_rows entries: the (frame s, class c) block (see VDET_LAYOUT_*) holds
+ *                the kept rows in descending score (ties: ascending row), then -1 padding
+ *   keep_cnt     int32, C*S entries
+ *   keep_mask    optional uint8, C*n_rows entries (1 = kept), same blocks, indexed by packed row
  *   status       [1] uint32, OR-ed with VDET_STATUS_* (never cleared by the library)
- * max_seg_len: an upper bound of the longest frame (chooses the kernel variant); this
- * build supports max_seg_len <= 4096.
+ * max_seg_len: an upper bound of the longest frame (chooses the kernel variant): <= 1024 keeps the
+ * frame's bit matrix in shared memory, <= 2048 uses `ws` (vdet_nms_frames_workspace_bytes);
+ * longer frames are handled by the drop-in entry points below (any length, one class).
  * ------------------------------------------------------------------------------------- */
 size_t vdet_nms_frames_workspace_bytes(int max_seg_len, int n_classes, int device);
 int vdet_nms_frames_f32(const float* boxes, int box_ld,
@@ -86,7 +94,7 @@ int vdet_nms_frames_f32(const float* boxes, int box_ld,
                         const int32_t* seg_offsets, int n_segs, int max_seg_len,
                         const int32_t* row_ids, int n_classes, double thresh,
                         int32_t* keep_idx, int32_t* keep_cnt, uint8_t* keep_mask,
-                        int64_t n_rows, uint32_t* status,
+                        int64_t n_rows, int out_layout, uint32_t* status,
                         void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
@@ -118,7 +126,8 @@ int64_t vdet_track_det_nms_f32(const float* tracks, int64_t q, int tracks_ld,
  *                         vdet_segment_by_frame
  *   keep       [m] uint8, updated in place
  * track_boxes [q,4] float32 with track_seg[q] = frame SEGMENT index (or -1: frame has no
- * dets).  Boxes are applied in array order; two boxes on the same frame are sequenced.
+ * dets).  The boxes of one call must lie on DISTINCT frames (one tracklet); successive calls are
+ * sequenced by the stream, which preserves the reference's per-box order.
  * ------------------------------------------------------------------------------------- */
 int vdet_track_nms_step_f32(const float* det_info, int64_t m,
                             const int32_t* seg_offsets, const int32_t* row_ids, int n_segs,
@@ -210,6 +219,16 @@ int vdet_temporal_conv1d(const void* x, void* out, int dtype, int64_t n_rows, in
 int vdet_threshold_topk_f32(const float* scores, const int32_t* seg_offsets, int n_segs,
                             int max_seg_len, int n_classes, float thresh, int k,
                             int32_t* idx_out, int32_t* cnt_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Stable sort of (score, id) pairs by DESCENDING score (equal scores keep their input order).
+ * The merge step of a frame-sharded vid_nms: every rank all-gathers its kept (score, global row)
+ * list and sorts the concatenation into the reference's global keep order (utils/nms.pyx:80,97).
+ * ------------------------------------------------------------------------------------- */
+size_t vdet_sort_workspace_bytes(int64_t n);
+int vdet_sort_by_score_desc_f32(const float* scores, const int64_t* ids, int64_t n,
+                                float* scores_out, int64_t* ids_out,
+                                void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

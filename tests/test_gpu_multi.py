@@ -62,6 +62,14 @@ def _worker(rank, world, port, T, N, C, thr, out_dir):
     pp = ShardedVideoPostProcessor(e - a, N, C, thr, dev)
     pp.pp.stage(b[a:e], s[a:e])
     res = pp.step_host()
+    # frame-sharded vid_nms of one class with the global keep-order merge
+    from vdetlib_b200.dist import sharded_vid_nms
+    s_glob = s[:, :, 0] + np.arange(T)[:, None] * 1e-5                      # unique across the video
+    dets = np.concatenate([np.repeat(np.arange(1, T + 1), N)[:, None], b.reshape(-1, 4), s_glob.reshape(-1, 1)],
+                          axis=1).astype(np.float32)
+    merged = sharded_vid_nms(torch.from_numpy(dets[a * N:e * N]).to(dev), 0.3, a * N)
+    res = dict(res)
+    res["vid_keep"] = merged.cpu().numpy()
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), **{k: np.array(v) for k, v in res.items()})
     dist.barrier()
     dist.destroy_process_group()
@@ -79,11 +87,17 @@ def test_sharded_pipeline_matches_single_gpu(tmp_path, world):
     sock = socket.socket(); sock.bind(("127.0.0.1", 0)); port = sock.getsockname()[1]; sock.close()
     mp.spawn(_worker, args=(world, port, T, N, C, thr, str(tmp_path)), nprocs=world, join=True)
     per = T // world
+    from oracle import c_oracle
+    s_glob = s[:, :, 0] + np.arange(T)[:, None] * 1e-5
+    dets = np.concatenate([np.repeat(np.arange(1, T + 1), N)[:, None], b.reshape(-1, 4), s_glob.reshape(-1, 1)],
+                          axis=1).astype(np.float32)
+    want_keep = c_oracle.vid_nms(dets, 0.3)
     for r in range(world):
         got = np.load(os.path.join(str(tmp_path), "rank%d.npz" % r))
+        assert got["vid_keep"].tolist() == want_keep                            # same global order on every rank
         lo, hi = r * per * N, (r + 1) * per * N
-        assert np.array_equal(got["keep_cnt"], cnt[:, r * per:(r + 1) * per])
-        assert np.array_equal(got["keep_mask"], mask[:, lo:hi])
+        assert np.array_equal(got["keep_cnt"], cnt[:, r * per:(r + 1) * per].T)                  # [frames, C]
+        assert np.array_equal(got["keep_mask"], mask[:, lo:hi].reshape(C, per, N).transpose(1, 0, 2))
         assert np.array_equal(got["link_iou"], iou[lo:hi])
         want = succ[lo:hi].astype(np.int64)
         local = np.where(want >= 0, want - lo, -1)

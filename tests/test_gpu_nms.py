@@ -217,3 +217,53 @@ def test_nms_any_length_frames():
     z = np.concatenate([d[:3000], np.asarray([[5, 5, 4, 4, 0.001], [7, 7, 6, 6, 0.0005]], np.float32)])
     with pytest.raises(ZeroDivisionError):
         gpu.nms(z, 0.3)
+
+
+def test_frame_major_layout_and_pipelined_postprocessor():
+    """Frame-major outputs (ragged frames) and the chunk-pipelined host API equal the oracle."""
+    from vdetlib_b200.vdet.video_det import VideoPostProcessor
+    counts = np.asarray([5, 0, 64, 300, 33, 1, 128, 7], np.int32)
+    T, nmax, C = len(counts), 300, 4
+    b, s = synth.boxes_scores(T, nmax, C, seed=91)
+    km, ki, kc = c_oracle.nms_frames(b, s, 0.3, counts)
+    rows_b = np.concatenate([b[t, :counts[t]] for t in range(T)])
+    rows_s = np.concatenate([s[t, :counts[t]] for t in range(T)])
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    dev = torch.device("cuda")
+    keep_idx, keep_cnt, keep_mask, status = ops.nms_frames(
+        torch.from_numpy(rows_b).to(dev), torch.from_numpy(rows_s).to(dev), torch.from_numpy(off).to(dev),
+        0.3, int(counts.max()), want_mask=True, frame_major_out=True)
+    assert ops.raise_for_status(status) == 0
+    assert np.array_equal(keep_cnt.cpu().numpy(), kc)                       # [S, C]
+    gi, gm = keep_idx.cpu().numpy(), keep_mask.cpu().numpy()
+    for t in range(T):
+        n = counts[t]
+        for c in range(C):
+            blk = off[t] * C + c * n
+            want = np.where(ki[t, c, :n] >= 0, ki[t, c, :n] + off[t], -1)
+            assert np.array_equal(gi[blk:blk + n], want)
+            assert np.array_equal(gm[blk:blk + n], km[t, c, :n])
+    # the public host API, pipelined over 3 uneven chunks
+    T2, N2, C2 = 10, 120, 5
+    b2, s2 = synth.boxes_scores(T2, N2, C2, seed=92)
+    km2, ki2, kc2 = c_oracle.nms_frames(b2, s2, 0.3)
+    ls, lb = c_oracle.link_f32(b2)
+    for n_chunks in (1, 3, 10):
+        pp = VideoPostProcessor(T2, N2, C2, 0.3, n_chunks=n_chunks)
+        out = pp.run_host(b2, s2)
+        assert np.array_equal(out["keep_mask"], km2) and np.array_equal(out["keep_cnt"], kc2)
+        got = out["succ"][:(T2 - 1) * N2].reshape(T2 - 1, N2) - np.arange(1, T2)[:, None] * N2
+        assert np.array_equal(got, ls) and np.array_equal(out["link_iou"][:(T2 - 1) * N2].reshape(T2 - 1, N2), lb)
+        dev_out = pp.run_device(pp.d_boxes, pp.d_scores)
+        assert np.array_equal(dev_out["keep_idx"].cpu().numpy(), np.where(ki2 >= 0, ki2 + (np.arange(T2) * N2)[:, None, None], -1))
+
+
+def test_sort_by_score_desc():
+    rng = np.random.default_rng(6)
+    for n in (1, 5, 2048, 2049, 100000):
+        sc = rng.uniform(-1, 1, n).astype(np.float32)
+        sc[rng.integers(0, n, max(n // 10, 1))] = 0.25                      # ties keep their input order
+        ids = rng.integers(0, 1 << 40, n)
+        so, io = ops.sort_by_score_desc(torch.from_numpy(sc).cuda(), torch.from_numpy(ids).cuda())
+        order = np.argsort(-sc, kind="stable")
+        assert np.array_equal(so.cpu().numpy(), sc[order]) and np.array_equal(io.cpu().numpy(), ids[order])

@@ -16,6 +16,7 @@ STATUS_ALL_MISSING = 2
 DTYPE_F32, DTYPE_F64 = 0, 1
 POOL_ARGMAX_SCORE, POOL_ARGMAX_IOU = 0, 1
 PAD_ZERO, PAD_EDGE = 0, 1
+LAYOUT_CLASS_MAJOR, LAYOUT_FRAME_MAJOR = 0, 1
 
 _c = ctypes
 _vp, _i32, _i64, _f64, _f32, _sz = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_double, _c.c_float, _c.c_size_t
@@ -27,7 +28,7 @@ SIGNATURES = {
     "vdet_sm_count": (_i32, [_i32]),
     "vdet_nms_frames_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "vdet_nms_frames_f32": (_i32, [_vp, _i32, _vp, _i64, _i64, _vp, _i32, _i32, _vp, _i32, _f64,
-                                   _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
+                                   _vp, _vp, _vp, _i64, _i32, _vp, _vp, _sz, _vp]),
     "vdet_nms_workspace_bytes": (_sz, [_i64, _i32]),
     "vdet_nms_f32": (_i64, [_vp, _i64, _i32, _f64, _vp, _vp, _vp, _sz, _vp]),
     "vdet_vid_nms_f32": (_i64, [_vp, _i64, _i32, _f64, _vp, _vp, _vp, _sz, _vp]),
@@ -44,6 +45,8 @@ SIGNATURES = {
     "vdet_score_completion": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _f64, _vp, _vp]),
     "vdet_temporal_maxpool": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _i32, _f64, _vp]),
     "vdet_temporal_conv1d": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "vdet_sort_workspace_bytes": (_sz, [_i64]),
+    "vdet_sort_by_score_desc_f32": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "vdet_threshold_topk_f32": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _i32, _vp, _vp, _vp]),
 }
 

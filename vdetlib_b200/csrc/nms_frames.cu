@@ -39,6 +39,7 @@ struct NmsFramesParams {
     int npad;          // big-frame variant: power-of-two sort length >= nb
     int fast_filter;   // 1: division-free threshold filter allowed (2^-20 <= T <= 2)
     int so_words;      // per-warp order scratch: (nb/32)*33 words
+    int frame_major;   // output layout (VDET_LAYOUT_*)
 };
 
 // One 32x32 tile of the suppression bit matrix: lane = row i (box in registers), the 32 columns
@@ -286,8 +287,9 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 3 : 1)) nms_frames_
             // the next kept box, its mask row is OR-ed in and kills later lanes of the same group.
             uint32_t rem = 0;        // lane w: word w of the removed set
             int cnt = 0;
-            int32_t* out_idx = p.keep_idx + (int64_t)c * p.n_rows + off;
-            uint8_t* out_m = p.keep_mask ? p.keep_mask + (int64_t)c * p.n_rows + off : nullptr;
+            const int64_t blk = p.frame_major ? ((int64_t)off * C + (int64_t)c * n) : ((int64_t)c * p.n_rows + off);
+            int32_t* out_idx = p.keep_idx + blk;
+            uint8_t* out_m = p.keep_mask ? p.keep_mask + blk : nullptr;
             const unsigned lt = lanemask_lt();
 #pragma unroll 1
             for (int g = 0; g < Wn; ++g) {
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 3 : 1)) nms_frames_
                 cnt += __popc(kgrp);
             }
             for (int e = cnt + lane; e < n; e += 32) out_idx[e] = -1;
-            if (lane == 0) p.keep_cnt[(int64_t)c * p.n_segs + seg] = cnt;
+            if (lane == 0) p.keep_cnt[p.frame_major ? ((int64_t)seg * C + c) : ((int64_t)c * p.n_segs + seg)] = cnt;
             __syncwarp();
         }
         __syncthreads();   // smem is reused by the next frame
@@ -458,7 +460,8 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_frames_big_kernel(const NmsFr
             uint32_t rem0 = 0, rem1 = 0, kept0 = 0, kept1 = 0;
             int cnt = 0;
             int32_t buf = -1;
-            int32_t* out_idx = p.keep_idx + (int64_t)c * p.n_rows + off;
+            const int64_t blk = p.frame_major ? ((int64_t)off * C + (int64_t)c * n) : ((int64_t)c * p.n_rows + off);
+            int32_t* out_idx = p.keep_idx + blk;
             for (int k = 0; k < n; ++k) {
                 const uint32_t i = (uint32_t)keys[k];                       // broadcast read
                 const uint32_t w = i >> 5;
@@ -496,10 +499,10 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_frames_big_kernel(const NmsFr
                 const int done = cnt & ~31;
                 if (done + lane < cnt) out_idx[done + lane] = buf;
                 for (int e = cnt + lane; e < n; e += 32) out_idx[e] = -1;
-                if (lane == 0) p.keep_cnt[(int64_t)c * p.n_segs + seg] = cnt;
+                if (lane == 0) p.keep_cnt[p.frame_major ? ((int64_t)seg * C + c) : ((int64_t)c * p.n_segs + seg)] = cnt;
             }
             if (p.keep_mask) {
-                uint8_t* out_m = p.keep_mask + (int64_t)c * p.n_rows + off;
+                uint8_t* out_m = p.keep_mask + blk;
                 for (int wi = 0; wi < Wn; ++wi) {
                     const uint32_t kw = __shfl_sync(FULL, (wi & 32) ? kept1 : kept0, wi & 31);
                     const int e = wi * 32 + lane;
@@ -532,8 +535,9 @@ extern "C" int vdet_nms_frames_f32(const float* boxes, int box_ld,
                                    const int32_t* seg_offsets, int n_segs, int max_seg_len,
                                    const int32_t* row_ids, int n_classes, double thresh,
                                    int32_t* keep_idx, int32_t* keep_cnt, uint8_t* keep_mask,
-                                   int64_t n_rows, uint32_t* status,
+                                   int64_t n_rows, int out_layout, uint32_t* status,
                                    void* ws, size_t ws_bytes, void* stream) {
+    VDET_REQUIRE(out_layout == VDET_LAYOUT_CLASS_MAJOR || out_layout == VDET_LAYOUT_FRAME_MAJOR, "nms_frames: bad out_layout");
     VDET_REQUIRE(n_segs >= 0 && n_classes >= 1 && n_rows >= 0 && max_seg_len >= 0, "nms_frames: negative size");
     VDET_REQUIRE(box_ld >= 4, "nms_frames: box_ld must be >= 4");
     VDET_REQUIRE(status != nullptr && keep_idx != nullptr && keep_cnt != nullptr, "nms_frames: null output");
@@ -548,6 +552,7 @@ extern "C" int vdet_nms_frames_f32(const float* boxes, int box_ld,
     }
     NmsFramesParams p;
     p.gmask = nullptr; p.npad = 0;
+    p.frame_major = (out_layout == VDET_LAYOUT_FRAME_MAJOR) ? 1 : 0;
     {
         const float Tf = thresh_ceil_f32(thresh);
         p.fast_filter = (Tf >= 9.5367431640625e-07f && Tf <= 2.0f) ? 1 : 0;

@@ -348,8 +348,8 @@ int64_t nms_core(const float* dets, int64_t n, int ld, const float* frames, int 
             if (!c.ok()) { set_error("nms: workspace too small"); return VDET_ERR_WORKSPACE; }
         }
         rc = vdet_nms_frames_f32(dets + box_col, ld, dets + score_col, ld, 0, seg_offsets, n_segs, max_len,
-                                 row_ids_arg, 1, thresh, keep_idx, keep_cnt, nullptr, n_packed, status,
-                                 fws, fws_bytes, st);
+                                 row_ids_arg, 1, thresh, keep_idx, keep_cnt, nullptr, n_packed, VDET_LAYOUT_CLASS_MAJOR,
+                                 status, fws, fws_bytes, st);
         if (rc != VDET_OK) return rc;
     } else {
         // any-length path: order every frame by descending score, gather, walk on the fly
@@ -449,4 +449,53 @@ extern "C" int64_t vdet_track_det_nms_f32(const float* tracks, int64_t q, int tr
     VDET_CUDA(cudaMemcpy(&s1, status1, sizeof(uint32_t), cudaMemcpyDeviceToHost));
     *status_host = s1 | s2;
     return r;
+}
+
+
+// ---- stable descending sort of (score, id) pairs (cross-rank keep-list merge) ----------------
+namespace vdet {
+__global__ void k_sort_keys(const float* __restrict__ scores, int64_t n, uint32_t* __restrict__ keys,
+                            uint32_t* __restrict__ vals) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    keys[p] = f32_key_desc(scores[p]);
+    vals[p] = (uint32_t)p;
+}
+__global__ void k_sort_gather(const uint32_t* __restrict__ perm, const float* __restrict__ scores,
+                              const int64_t* __restrict__ ids, int64_t n, float* __restrict__ scores_out,
+                              int64_t* __restrict__ ids_out) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t q = perm[p];
+    scores_out[p] = scores[q];
+    ids_out[p] = ids[q];
+}
+}  // namespace vdet
+
+extern "C" size_t vdet_sort_workspace_bytes(int64_t n) {
+    if (n < 1) n = 1;
+    return 4 * (size_t)(n + 1) * 4 + radix_scratch_elems(n) * 4 + 8 * 256;
+}
+
+extern "C" int vdet_sort_by_score_desc_f32(const float* scores, const int64_t* ids, int64_t n,
+                                           float* scores_out, int64_t* ids_out,
+                                           void* ws, size_t ws_bytes, void* stream) {
+    VDET_REQUIRE(n >= 0 && n < 0x7fffffff, "sort_by_score: bad size");
+    if (n == 0) return VDET_OK;
+    VDET_REQUIRE(scores != scores_out && ids != ids_out, "sort_by_score: in-place sort is not supported");
+    cudaStream_t st = (cudaStream_t)stream;
+    WsCarver c(ws, ws_bytes);
+    uint32_t* k = c.take<uint32_t>(n + 1);
+    uint32_t* v = c.take<uint32_t>(n + 1);
+    uint32_t* ka = c.take<uint32_t>(n + 1);
+    uint32_t* va = c.take<uint32_t>(n + 1);
+    uint32_t* radix = c.take<uint32_t>(radix_scratch_elems(n));
+    if (!c.ok()) { set_error("sort_by_score: workspace too small"); return VDET_ERR_WORKSPACE; }
+    k_sort_keys<<<blocks_for(n), 256, 0, st>>>(scores, n, k, v);
+    VDET_LAUNCH_CHECK();
+    const int flip = radix_sort_pairs(k, v, ka, va, n, 0, 32, radix, st);
+    if (flip < 0) return flip;
+    k_sort_gather<<<blocks_for(n), 256, 0, st>>>(flip ? va : v, scores, ids, n, scores_out, ids_out);
+    VDET_LAUNCH_CHECK();
+    return VDET_OK;
 }

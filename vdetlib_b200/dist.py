@@ -64,34 +64,82 @@ class ShardedVideoPostProcessor(object):
     """The per-rank step of the multi-GPU pipeline: NMS of the local frames, boundary exchange,
     link (local frames + halo).  Weak scaling: every rank holds ``n_frames`` frames."""
 
-    def __init__(self, n_frames, n_boxes, n_classes, nms_thresh=0.3, device=None, group=None):
+    def __init__(self, n_frames, n_boxes, n_classes, nms_thresh=0.3, device=None, group=None, n_chunks=4):
         from .vdet.video_det import VideoPostProcessor
-        self.pp = VideoPostProcessor(n_frames, n_boxes, n_classes, nms_thresh, device)
+        self.pp = VideoPostProcessor(n_frames, n_boxes, n_classes, nms_thresh, device, n_chunks=n_chunks)
         self.exchange = BoundaryExchange(n_boxes, self.pp.device, group)
         self.side = torch.cuda.Stream(device=self.pp.device)
         self.n_boxes = n_boxes
+
+    def _exchange(self, d_first_frame):
+        """Boundary all-gather on the side stream; returns (halo, join) -- call join() before the link."""
+        main = torch.cuda.current_stream()
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            handle = self.exchange.start(d_first_frame)
+            halo = self.exchange.finish(handle, count_hint=self.n_boxes)
+        return halo
 
     def step_device(self, d_boxes, d_scores):
         """Device-resident inputs; returns the result dict of VideoPostProcessor.run_device."""
         from . import ops
         pp = self.pp
         main = torch.cuda.current_stream()
-        self.side.wait_stream(main)
-        with torch.cuda.stream(self.side):
-            handle = self.exchange.start(d_boxes[:self.n_boxes])
-        keep_idx, keep_cnt, keep_mask, _ = ops.nms_frames(
-            d_boxes, d_scores, pp.seg_offsets, pp.nms_thresh, pp.N, want_mask=True, status=pp.status)
-        with torch.cuda.stream(self.side):
-            halo = self.exchange.finish(handle, count_hint=self.n_boxes)
+        halo = self._exchange(d_boxes[:self.n_boxes])          # overlaps the NMS kernel
+        out = ops.nms_frames(d_boxes, d_scores, pp.seg_offsets, pp.nms_thresh, pp.N, want_mask=True,
+                             status=pp.status, frame_major_out=True, out=(pp.d_idx, pp.d_cnt, pp.d_mask))
         main.wait_stream(self.side)
         succ, link_iou = ops.link_frames(d_boxes, pp.seg_offsets, pp.N, halo)
-        return {"keep_idx": keep_idx, "keep_cnt": keep_cnt, "keep_mask": keep_mask,
-                "succ": succ, "link_iou": link_iou}
+        res = pp._views(out)
+        res.update(succ=succ, link_iou=link_iou)
+        return res
 
     def step_host(self):
-        """The end-to-end step: H2D from the pinned staging buffers (fill them with
+        """The end-to-end step: pipelined H2D from the pinned staging buffers (fill them with
         ``self.pp.stage(boxes, scores)``), kernels + boundary exchange, D2H of the results."""
         pp = self.pp
-        pp.d_boxes.copy_(pp.h_boxes, non_blocking=True)
-        pp.d_scores.copy_(pp.h_scores, non_blocking=True)
-        return pp.read_back(self.step_device(pp.d_boxes, pp.d_scores))
+        res = pp.run_staged(halo_fn=self._halo_then_join)
+        return res
+
+    def _halo_then_join(self, d_first_frame):
+        halo = self._exchange(d_first_frame)
+        # the compute stream must not start the link before the all-gather finished; the wait is
+        # enqueued now (cheap: the exchange is ~20 us and the NMS chunks run in between anyway)
+        torch.cuda.current_stream().wait_stream(self.side)
+        return halo
+
+
+def sharded_vid_nms(dets_local, thresh, row_offset, group=None):
+    """vid_nms (utils/nms.pyx:71-125) of a video whose rows are sharded by frame over the ranks.
+
+    ``dets_local`` [M_r, 6] float32 CUDA tensor = this rank's rows (whole frames only: a frame must
+    not straddle ranks), ``row_offset`` = global index of its first row.  Suppression is per
+    frame, hence local; only the reference's GLOBAL descending-score keep order needs the other
+    ranks: one all-gather of the kept (score, global row) lists (padded to the longest) and one
+    stable sort.  Every rank returns the same int64 tensor of global row indices.
+    """
+    from . import ops
+    keep = ops.vid_nms(dets_local, thresh)                         # local rows, local score order
+    scores = dets_local[:, 5].contiguous()[keep]
+    rows = keep + int(row_offset)
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return rows
+    world = dist.get_world_size(group)
+    dev = dets_local.device
+    n_local = torch.tensor([rows.numel()], dtype=torch.int64, device=dev)
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, n_local, group=group)
+    counts = counts.cpu().tolist()
+    cap = max(max(counts), 1)
+    send_s = torch.zeros(cap, dtype=torch.float32, device=dev)
+    send_r = torch.zeros(cap, dtype=torch.int64, device=dev)
+    send_s[:rows.numel()] = scores
+    send_r[:rows.numel()] = rows
+    all_s = torch.empty(world * cap, dtype=torch.float32, device=dev)
+    all_r = torch.empty(world * cap, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_s, send_s, group=group)
+    dist.all_gather_into_tensor(all_r, send_r, group=group)
+    cat_s = torch.cat([all_s[r * cap:r * cap + counts[r]] for r in range(world)])
+    cat_r = torch.cat([all_r[r * cap:r * cap + counts[r]] for r in range(world)])
+    _, merged = ops.sort_by_score_desc(cat_s, cat_r)
+    return merged

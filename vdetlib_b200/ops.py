@@ -69,11 +69,14 @@ def seg_offsets_uniform(n_frames, n_per_frame, device):
 # NMS
 # ------------------------------------------------------------------------------------------
 def nms_frames(boxes, scores, seg_offsets, thresh, max_seg_len, row_ids=None, want_mask=False,
-               status=None, class_major=False):
+               status=None, class_major=False, frame_major_out=False, out=None):
     """Greedy NMS of every (frame, class) on class-shared boxes (utils/nms.pyx:43-66 per problem).
 
     boxes [n,4] f32; scores [n,C] f32 (or [C,n] with class_major=True, or [n]);
-    seg_offsets [S+1] i32.  Returns (keep_idx [C,n] i32, keep_cnt [C,S] i32, keep_mask|None, status).
+    seg_offsets [S+1] i32.  Returns (keep_idx i32, keep_cnt i32, keep_mask|None, status):
+    class-major outputs [C,n] / [C,S] by default; with frame_major_out=True flat [n*C] buffers
+    whose (frame s, class c) block sits at seg_offsets[s]*C + c*n_s, and keep_cnt [S,C].
+    ``out=(keep_idx, keep_cnt, keep_mask)`` writes into caller-provided buffers.
     """
     lib = _lib.load()
     _need(boxes, "boxes", torch.float32, 2)
@@ -90,9 +93,16 @@ def nms_frames(boxes, scores, seg_offsets, thresh, max_seg_len, row_ids=None, wa
         C, ldr, ldc = scores.shape[1], scores.shape[1], 1
     S = seg_offsets.numel() - 1
     dev = boxes.device
-    keep_idx = torch.empty((C, n), dtype=torch.int32, device=dev)
-    keep_cnt = torch.empty((C, S), dtype=torch.int32, device=dev)
-    keep_mask = torch.empty((C, n), dtype=torch.uint8, device=dev) if want_mask else None
+    if out is not None:
+        keep_idx, keep_cnt, keep_mask = out
+    elif frame_major_out:
+        keep_idx = torch.empty(C * n, dtype=torch.int32, device=dev)
+        keep_cnt = torch.empty((S, C), dtype=torch.int32, device=dev)
+        keep_mask = torch.empty(C * n, dtype=torch.uint8, device=dev) if want_mask else None
+    else:
+        keep_idx = torch.empty((C, n), dtype=torch.int32, device=dev)
+        keep_cnt = torch.empty((C, S), dtype=torch.int32, device=dev)
+        keep_mask = torch.empty((C, n), dtype=torch.uint8, device=dev) if want_mask else None
     if status is None:
         status = new_status(dev)
     if row_ids is not None:
@@ -103,8 +113,9 @@ def nms_frames(boxes, scores, seg_offsets, thresh, max_seg_len, row_ids=None, wa
         ws = _workspace(ws_bytes, dev)
     rc = lib.vdet_nms_frames_f32(_ptr(boxes), 4, _ptr(scores), ldr, ldc, _ptr(seg_offsets), S,
                                  int(max_seg_len), _ptr(row_ids), C, float(thresh),
-                                 _ptr(keep_idx), _ptr(keep_cnt), _ptr(keep_mask), n, _ptr(status),
-                                 _ptr(ws), ws_bytes, _stream())
+                                 _ptr(keep_idx), _ptr(keep_cnt), _ptr(keep_mask), n,
+                                 _lib.LAYOUT_FRAME_MAJOR if frame_major_out else _lib.LAYOUT_CLASS_MAJOR,
+                                 _ptr(status), _ptr(ws), ws_bytes, _stream())
     _lib.check(rc, "nms_frames")
     return keep_idx, keep_cnt, keep_mask, status
 
@@ -344,6 +355,20 @@ def threshold_topk(scores, seg_offsets, max_seg_len, thresh=0.05, k=100):
                                      int(k), _ptr(idx), _ptr(cnt), _stream())
     _lib.check(rc, "threshold_topk")
     return idx, cnt
+
+
+def sort_by_score_desc(scores, ids):
+    """Stable sort of (score f32, id i64) pairs by descending score (ties keep input order)."""
+    lib = _lib.load()
+    _need(scores, "scores", torch.float32, 1)
+    _need(ids, "ids", torch.int64, 1)
+    scores, ids = scores.contiguous(), ids.contiguous()
+    n = scores.numel()
+    so, io = torch.empty_like(scores), torch.empty_like(ids)
+    ws = _workspace(lib.vdet_sort_workspace_bytes(n) + 1024, scores.device)
+    _lib.check(lib.vdet_sort_by_score_desc_f32(_ptr(scores), _ptr(ids), n, _ptr(so), _ptr(io), _ptr(ws), ws.numel(),
+                                               _stream()), "sort_by_score_desc")
+    return so, io
 
 
 def to_device(array, dtype=None, device=None):

@@ -59,37 +59,54 @@ class VideoPostProcessor(object):
     """NMS (all classes) + frame-to-frame link for one video shard of fixed shape.
 
     Input: boxes [T, N, 4] float32 and scores [T, N, C] float32 on the HOST (any array-like;
-    copied through pinned staging buffers) or already on the device.  Output (device tensors,
-    or host arrays from :meth:`run_host`):
+    copied through pinned staging buffers) or already on the device.  Output (device tensors from
+    :meth:`run_device`, host arrays from :meth:`run_host` / :meth:`run_staged`), frame-major:
 
-      keep_mask [C, T*N] uint8   1 = detection survives per-frame NMS for that class
-      keep_cnt  [C, T]   int32   survivors per (class, frame)
-      keep_idx  [C, T*N] int32   surviving rows per frame in descending score, -1 padded
-      succ      [T*N]    int32   packed row of the best-IoU box in the next frame (-1: none)
-      link_iou  [T*N]    float32 that IoU
+      keep_mask [T, C, N] uint8   1 = detection survives per-frame NMS for that class
+      keep_cnt  [T, C]    int32   survivors per (frame, class)
+      keep_idx  [T, C, N] int32   surviving rows of the frame in descending score, -1 padded
+                                  (device only; not copied back by default)
+      succ      [T*N]     int32   packed row of the best-IoU box in the next frame (-1: none)
+      link_iou  [T*N]     float32 that IoU
 
     ``halo`` (boxes of the first frame of the NEXT shard, [H,4]) links the shard's last frame
     across a shard boundary (see vdetlib_b200.dist).
+
+    The host path is pipelined: the shard is cut into ``n_chunks`` frame ranges; chunk k's
+    host->device copy (copy stream), NMS (compute stream) and result read-back (read-back stream)
+    overlap with the neighbouring chunks', so PCIe in both directions and the SMs are busy at the
+    same time.  Frame-major outputs make every chunk a contiguous byte range.
     """
 
-    def __init__(self, n_frames, n_boxes, n_classes, nms_thresh=0.3, device=None, want_idx=True):
+    def __init__(self, n_frames, n_boxes, n_classes, nms_thresh=0.3, device=None, n_chunks=4):
         self.T, self.N, self.C = int(n_frames), int(n_boxes), int(n_classes)
         self.nms_thresh = float(nms_thresh)
         self.device = device or torch.device("cuda", torch.cuda.current_device())
-        self.want_idx = want_idx
-        rows = self.T * self.N
-        self.seg_offsets = ops.seg_offsets_uniform(self.T, self.N, self.device)
-        self.d_boxes = torch.empty((rows, 4), dtype=torch.float32, device=self.device)
-        self.d_scores = torch.empty((rows, self.C), dtype=torch.float32, device=self.device)
+        T, N, C = self.T, self.N, self.C
+        rows = T * N
+        dev = self.device
+        self.seg_offsets = ops.seg_offsets_uniform(T, N, dev)
+        self.d_boxes = torch.empty((rows, 4), dtype=torch.float32, device=dev)
+        self.d_scores = torch.empty((rows, C), dtype=torch.float32, device=dev)
+        self.d_idx = torch.empty(rows * C, dtype=torch.int32, device=dev)
+        self.d_mask = torch.empty(rows * C, dtype=torch.uint8, device=dev)
+        self.d_cnt = torch.empty((T, C), dtype=torch.int32, device=dev)
         self.h_boxes = torch.empty((rows, 4), dtype=torch.float32).pin_memory()
-        self.h_scores = torch.empty((rows, self.C), dtype=torch.float32).pin_memory()
-        self.h_mask = torch.empty((self.C, rows), dtype=torch.uint8).pin_memory()
-        self.h_cnt = torch.empty((self.C, self.T), dtype=torch.int32).pin_memory()
+        self.h_scores = torch.empty((rows, C), dtype=torch.float32).pin_memory()
+        self.h_mask = torch.empty(rows * C, dtype=torch.uint8).pin_memory()
+        self.h_cnt = torch.empty((T, C), dtype=torch.int32).pin_memory()
         self.h_succ = torch.empty(rows, dtype=torch.int32).pin_memory()
         self.h_iou = torch.empty(rows, dtype=torch.float32).pin_memory()
-        self.status = ops.new_status(self.device)
+        self.status = ops.new_status(dev)
+        # frame ranges of the pipeline chunks
+        n_chunks = max(1, min(int(n_chunks), T))
+        edges = [round(k * T / n_chunks) for k in range(n_chunks + 1)]
+        self.chunks = [(edges[k], edges[k + 1]) for k in range(n_chunks) if edges[k + 1] > edges[k]]
+        self.chunk_seg = {f1 - f0: ops.seg_offsets_uniform(f1 - f0, N, dev) for f0, f1 in self.chunks}
+        self.s_in = torch.cuda.Stream(device=dev)
+        self.s_out = torch.cuda.Stream(device=dev)
 
-    # bytes crossing PCIe per run_host() call
+    # bytes crossing PCIe per run_staged() call
     @property
     def h2d_bytes(self):
         return self.h_boxes.numel() * 4 + self.h_scores.numel() * 4
@@ -98,35 +115,62 @@ class VideoPostProcessor(object):
     def d2h_bytes(self):
         return self.h_mask.numel() + self.h_cnt.numel() * 4 + self.h_succ.numel() * 4 + self.h_iou.numel() * 4
 
+    def _views(self, out):
+        T, N, C = self.T, self.N, self.C
+        return {"keep_idx": out[0].view(T, C, N), "keep_cnt": out[1], "keep_mask": out[2].view(T, C, N)}
+
     def run_device(self, d_boxes, d_scores, halo=None):
-        """Device tensors in ([T*N,4], [T*N,C]), device tensors out; asynchronous."""
-        keep_idx, keep_cnt, keep_mask, _ = ops.nms_frames(
-            d_boxes, d_scores, self.seg_offsets, self.nms_thresh, self.N, want_mask=True, status=self.status)
+        """Device tensors in ([T*N,4], [T*N,C]), device tensors out; asynchronous, one launch each."""
+        out = ops.nms_frames(d_boxes, d_scores, self.seg_offsets, self.nms_thresh, self.N, want_mask=True,
+                             status=self.status, frame_major_out=True, out=(self.d_idx, self.d_cnt, self.d_mask))
         succ, link_iou = ops.link_frames(d_boxes, self.seg_offsets, self.N, halo)
-        return {"keep_idx": keep_idx, "keep_cnt": keep_cnt, "keep_mask": keep_mask,
-                "succ": succ, "link_iou": link_iou}
+        res = self._views(out)
+        res.update(succ=succ, link_iou=link_iou)
+        return res
 
     def stage(self, boxes, scores):
         """Copy host arrays into the pinned staging buffers (not part of the timed region)."""
         self.h_boxes.copy_(torch.as_tensor(np.ascontiguousarray(boxes, dtype=np.float32)).view(-1, 4))
         self.h_scores.copy_(torch.as_tensor(np.ascontiguousarray(scores, dtype=np.float32)).view(-1, self.C))
 
-    def run_staged(self, halo=None):
-        """H2D from the pinned buffers, kernels, D2H of the results; synchronises and returns host views."""
-        self.d_boxes.copy_(self.h_boxes, non_blocking=True)
-        self.d_scores.copy_(self.h_scores, non_blocking=True)
-        out = self.run_device(self.d_boxes, self.d_scores, halo)
-        return self.read_back(out)
-
-    def read_back(self, out):
-        """D2H of the results into the pinned buffers; synchronises and returns host views."""
-        self.h_mask.copy_(out["keep_mask"], non_blocking=True)
-        self.h_cnt.copy_(out["keep_cnt"], non_blocking=True)
-        self.h_succ.copy_(out["succ"], non_blocking=True)
-        self.h_iou.copy_(out["link_iou"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    def run_staged(self, halo=None, halo_fn=None):
+        """Pipelined H2D (pinned buffers) -> NMS per chunk -> D2H, then the link; synchronises and
+        returns host views.  ``halo_fn(d_first_frame_boxes)`` (optional) is called on the compute
+        stream once chunk 0 is on the device and returns the halo tensor (boundary exchange)."""
+        N, C = self.N, self.C
+        cur = torch.cuda.current_stream()
+        self.s_in.wait_stream(cur)
+        self.s_out.wait_stream(cur)
+        ev_in = []
+        with torch.cuda.stream(self.s_in):
+            for f0, f1 in self.chunks:
+                r0, r1 = f0 * N, f1 * N
+                self.d_boxes[r0:r1].copy_(self.h_boxes[r0:r1], non_blocking=True)
+                self.d_scores[r0:r1].copy_(self.h_scores[r0:r1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.s_in)
+                ev_in.append(ev)
+        for k, (f0, f1) in enumerate(self.chunks):
+            r0, r1 = f0 * N, f1 * N
+            cur.wait_event(ev_in[k])
+            if k == 0 and halo_fn is not None:
+                halo = halo_fn(self.d_boxes[:N])
+            ops.nms_frames(self.d_boxes[r0:r1], self.d_scores[r0:r1], self.chunk_seg[f1 - f0], self.nms_thresh, N,
+                           want_mask=True, status=self.status, frame_major_out=True,
+                           out=(self.d_idx[r0 * C:r1 * C], self.d_cnt[f0:f1], self.d_mask[r0 * C:r1 * C]))
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self.s_out.wait_event(ev)
+            with torch.cuda.stream(self.s_out):
+                self.h_mask[r0 * C:r1 * C].copy_(self.d_mask[r0 * C:r1 * C], non_blocking=True)
+                self.h_cnt[f0:f1].copy_(self.d_cnt[f0:f1], non_blocking=True)
+        succ, link_iou = ops.link_frames(self.d_boxes, self.seg_offsets, N, halo)
+        self.h_succ.copy_(succ, non_blocking=True)
+        self.h_iou.copy_(link_iou, non_blocking=True)
+        cur.wait_stream(self.s_out)
+        cur.synchronize()
         ops.raise_for_status(self.status)
-        return {"keep_mask": self.h_mask.numpy(), "keep_cnt": self.h_cnt.numpy(),
+        return {"keep_mask": self.h_mask.numpy().reshape(self.T, C, N), "keep_cnt": self.h_cnt.numpy(),
                 "succ": self.h_succ.numpy(), "link_iou": self.h_iou.numpy()}
 
     def run_host(self, boxes, scores, halo=None):
