@@ -201,8 +201,10 @@ int vdet_spatial_maxpool(const void* tub_boxes, const int32_t* tub_seg, int64_t 
  *   conv1d     : depthwise temporal convolution, the build-defined stand-in for
  *                score_conv_cls :15-51 (taps [n_channels, w]; row r uses channel r % n_channels)
  * ------------------------------------------------------------------------------------- */
+size_t vdet_score_completion_workspace_bytes(int64_t n_rows, int64_t L, int dtype);
 int vdet_score_completion(void* scores, int dtype, int64_t n_rows, int64_t L, int64_t ld,
-                          const int32_t* lengths, double miss_thr, uint32_t* status, void* stream);
+                          const int32_t* lengths, double miss_thr, uint32_t* status,
+                          void* ws, size_t ws_bytes, void* stream);
 int vdet_temporal_maxpool(const void* scores, void* out, int dtype, int64_t n_rows, int64_t L,
                           int64_t ld, const int32_t* lengths, int window, double pad, void* stream);
 int vdet_temporal_conv1d(const void* x, void* out, int dtype, int64_t n_rows, int64_t L,

@@ -114,79 +114,303 @@ __global__ void __launch_bounds__(TP_THREADS) temporal_conv1d_kernel(const T* __
     }
 }
 
+template <typename T> struct Vec16;
+template <> struct Vec16<float> { typedef float4 type; static constexpr int V = 4; };
+template <> struct Vec16<double> { typedef double2 type; static constexpr int V = 2; };
+
 // ---- score completion --------------------------------------------------------------------
-// One CTA per row, the whole row resident in shared memory.  A forward max-scan gives, for
-// every k, the last valid index <= k; a backward min-scan the next valid index >= k; every
-// missing element then evaluates the reference's closed form for its own run [i, j):
-//   leading run  -> s[j]            (tubelet_cls.py:293-295)
-//   trailing run -> s[i-1]          (:296-298)
+// do_score_completion (tubelet_cls.py:284-303): every maximal run [i, j) of missing scores
+// (score <= -10) is rewritten from its valid neighbours l = s[i-1], r = s[j]:
+//   leading run  -> r                       (:293-295)
+//   trailing run -> l                       (:296-298)
 //   interior     -> l + (r - l) * (k - i + 1) / (j - i + 1)     (:299-303)
+// Streaming formulation (one read + one write of the row, any row length): rows are cut into
+// 1024-element tiles.
+//   pass 1 (completion_bounds_kernel, one warp per tile): the nearest valid element to the LEFT of
+//          the tile and to the RIGHT of it (index + value) -- a ballot search that normally ends
+//          in its first 32-element probe -- goes to a small side buffer.  Reading neighbours in a
+//          separate pass keeps the in-place update of pass 2 race-free.
+//   pass 2 (completion_fill_kernel, one CTA per tile): 16-byte loads, block-wide max-scan of "last
+//          valid index" and min-scan of "next valid index" (warp shuffles + one shared-memory
+//          hop), closed form per missing element, 16-byte stores.
 constexpr int CP_THREADS = 256;
+constexpr int CP_ITEMS = 4;
+constexpr int CP_TILE = CP_THREADS * CP_ITEMS;
 
 template <typename T>
-__global__ void __launch_bounds__(CP_THREADS) score_completion_kernel(T* __restrict__ scores, int64_t L, int64_t ld,
-                                                                      const int32_t* __restrict__ lengths,
-                                                                      T miss_thr, int cap, uint32_t* status) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* s = reinterpret_cast<T*>(smem_raw);
-    int32_t* lastv = reinterpret_cast<int32_t*>(s + cap);
-    int32_t* nextv = lastv + cap;
-    __shared__ int32_t s_lv[CP_THREADS], s_fv[CP_THREADS];
-    const int64_t row = blockIdx.x;
+struct TileBounds { int32_t left_idx; int32_t right_idx; T left_val; T right_val; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) completion_bounds_kernel(const T* __restrict__ scores, int64_t L, int64_t ld,
+                                                                const int32_t* __restrict__ lengths,
+                                                                int tiles_per_row, int64_t n_tiles, T miss_thr,
+                                                                TileBounds<T>* __restrict__ bounds) {
+    const int lane = threadIdx.x & 31;
+    const int64_t tile_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tile_id >= n_tiles) return;
+    const int64_t row = tile_id / tiles_per_row;
+    const int tile = (int)(tile_id - row * tiles_per_row);
     const int len = (int)(lengths ? (int64_t)lengths[row] : L);
-    if (len <= 0) return;
+    const int t0 = tile * CP_TILE;
+    if (t0 >= len) return;
+    const int t1 = (t0 + CP_TILE < len) ? t0 + CP_TILE : len;
+    const T* g = scores + row * ld;
+    TileBounds<T> b;
+    b.left_idx = -1; b.right_idx = len; b.left_val = (T)0; b.right_val = (T)0;
+    for (int base = t0 - 1; base >= 0; base -= 32) {            // nearest valid element left of the tile
+        const int k = base - lane;
+        const T v = k >= 0 ? g[k] : (T)0;
+        const unsigned hit = __ballot_sync(FULL, k >= 0 && !(v <= miss_thr));
+        if (hit) {
+            const int l = __ffs(hit) - 1;
+            b.left_idx = base - l;
+            b.left_val = __shfl_sync(FULL, v, l);
+            break;
+        }
+    }
+    for (int base = t1; base < len; base += 32) {               // nearest valid element right of it
+        const int k = base + lane;
+        const T v = k < len ? g[k] : (T)0;
+        const unsigned hit = __ballot_sync(FULL, k < len && !(v <= miss_thr));
+        if (hit) {
+            const int l = __ffs(hit) - 1;
+            b.right_idx = base + l;
+            b.right_val = __shfl_sync(FULL, v, l);
+            break;
+        }
+    }
+    if (lane == 0) bounds[tile_id] = b;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CP_THREADS) completion_fill_kernel(T* __restrict__ scores, int64_t L, int64_t ld,
+                                                                     const int32_t* __restrict__ lengths,
+                                                                     int tiles_per_row, T miss_thr, int vec_ok,
+                                                                     const TileBounds<T>* __restrict__ bounds,
+                                                                     uint32_t* status) {
+    __shared__ T s_val[CP_TILE];
+    __shared__ int32_t s_wl[CP_THREADS / 32], s_wr[CP_THREADS / 32];
+    const int64_t tile_id = blockIdx.x;
+    const int64_t row = tile_id / tiles_per_row;
+    const int tile = (int)(tile_id - row * tiles_per_row);
+    const int len = (int)(lengths ? (int64_t)lengths[row] : L);
+    const int t0 = tile * CP_TILE;
+    if (t0 >= len) return;
     T* g = scores + row * ld;
-    const int tid = threadIdx.x;
-    for (int k = tid; k < len; k += CP_THREADS) s[k] = g[k];
-    __syncthreads();
-    // contiguous chunk per thread; odd chunk length keeps the strided passes conflict-free
-    const int ch = ((len + CP_THREADS - 1) / CP_THREADS) | 1;
-    const int b = tid * ch < len ? tid * ch : len;
-    const int e = b + ch < len ? b + ch : len;
-    int lv = -1, fv = 0x7fffffff;
-    for (int k = b; k < e; ++k) {
-        const bool valid = !(s[k] <= miss_thr);
-        if (valid) { lv = k; if (fv == 0x7fffffff) fv = k; }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int e0 = t0 + tid * CP_ITEMS;                       // this thread's 4 consecutive elements
+    T v[CP_ITEMS];
+    constexpr int V = 16 / sizeof(T);
+    if (vec_ok && e0 + CP_ITEMS <= len) {
+#pragma unroll
+        for (int q = 0; q < CP_ITEMS; q += V) {
+            const typename Vec16<T>::type x = *reinterpret_cast<const typename Vec16<T>::type*>(g + e0 + q);
+            const T* px = reinterpret_cast<const T*>(&x);
+#pragma unroll
+            for (int c = 0; c < V; ++c) v[q + c] = px[c];
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < CP_ITEMS; ++q) v[q] = (e0 + q < len) ? g[e0 + q] : (T)0;
     }
-    s_lv[tid] = lv;
-    s_fv[tid] = fv;
-    __syncthreads();
-    // exclusive max-scan of lv to the left, exclusive min-scan of fv to the right (256 entries)
-    int carry_l = -1, carry_r = 0x7fffffff;
-    for (int t = 0; t < tid; ++t) carry_l = max(carry_l, s_lv[t]);
-    for (int t = tid + 1; t < CP_THREADS; ++t) carry_r = min(carry_r, s_fv[t]);
-    for (int k = b; k < e; ++k) {
-        if (!(s[k] <= miss_thr)) carry_l = k;
-        lastv[k] = carry_l;
+    bool ok[CP_ITEMS];
+    int my_last = -1, my_first = 0x7fffffff;
+#pragma unroll
+    for (int q = 0; q < CP_ITEMS; ++q) {
+        ok[q] = (e0 + q < len) && !(v[q] <= miss_thr);
+        s_val[tid * CP_ITEMS + q] = v[q];
+        if (ok[q]) { my_last = e0 + q; if (my_first == 0x7fffffff) my_first = e0 + q; }
     }
-    for (int k = e - 1; k >= b; --k) {
-        if (!(s[k] <= miss_thr)) carry_r = k;
-        nextv[k] = carry_r;
+    // exclusive max-scan (threads before me) of my_last, exclusive min-scan (threads after me) of my_first
+    int incl_l = my_last, incl_r = my_first;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int a = __shfl_up_sync(FULL, incl_l, d);
+        const int c = __shfl_down_sync(FULL, incl_r, d);
+        if (lane >= d) incl_l = max(incl_l, a);
+        if (lane + d < 32) incl_r = min(incl_r, c);
     }
+    if (lane == 31) s_wl[warp] = incl_l;
+    if (lane == 0) s_wr[warp] = incl_r;
     __syncthreads();
-    for (int k = tid; k < len; k += CP_THREADS) {
-        const T v = s[k];
-        if (!(v <= miss_thr)) continue;        // valid (or NaN): untouched, as the reference
-        const int i = lastv[k] + 1;            // run start
-        const int j = nextv[k];                // first valid index after the run (or "none")
+    int before = __shfl_up_sync(FULL, incl_l, 1);
+    if (lane == 0) before = -1;
+    int after = __shfl_down_sync(FULL, incl_r, 1);
+    if (lane == 31) after = 0x7fffffff;
+    for (int w = 0; w < warp; ++w) before = max(before, s_wl[w]);
+    for (int w = warp + 1; w < CP_THREADS / 32; ++w) after = min(after, s_wr[w]);
+    const TileBounds<T> b = bounds[tile_id];
+    const int t1 = (t0 + CP_TILE < len) ? t0 + CP_TILE : len;
+    bool changed = false;
+    // last valid index at or before each element / next valid index at or after it
+    int lastv[CP_ITEMS], nextv[CP_ITEMS];
+    int run = before;
+#pragma unroll
+    for (int q = 0; q < CP_ITEMS; ++q) { if (ok[q]) run = e0 + q; lastv[q] = run; }
+    run = after;
+#pragma unroll
+    for (int q = CP_ITEMS - 1; q >= 0; --q) { if (ok[q]) run = e0 + q; nextv[q] = run; }
+#pragma unroll
+    for (int q = 0; q < CP_ITEMS; ++q) {
+        const int k = e0 + q;
+        if (k >= len || ok[q] || !(v[q] <= miss_thr)) continue;          // valid or NaN: untouched
+        int i, j;                 // run = [i, j)
+        T lft, rgt;
+        if (lastv[q] >= t0) { i = lastv[q] + 1; lft = s_val[lastv[q] - t0]; }
+        else { i = b.left_idx + 1; lft = b.left_val; }
+        if (nextv[q] < t1) { j = nextv[q]; rgt = s_val[nextv[q] - t0]; }
+        else { j = b.right_idx; rgt = b.right_val; }
         T r;
         if (i == 0) {
             if (j >= len) { if (k == 0) atomicOr(status, VDET_STATUS_ALL_MISSING); continue; }
-            r = s[j];
+            r = rgt;
         } else if (j >= len) {
-            r = s[i - 1];
+            r = lft;
         } else {
-            const T lft = s[i - 1], rgt = s[j];
             r = t_add(lft, t_div(t_mul(t_sub(rgt, lft), (T)(k - i + 1)), (T)(j - i + 1)));
         }
-        g[k] = r;
+        v[q] = r;
+        changed = true;
     }
+    // s_val is read above by other threads: writes go to global only
+    if (vec_ok && e0 + CP_ITEMS <= len) {
+        if (changed) {                                                    // untouched threads skip the store
+#pragma unroll
+            for (int q = 0; q < CP_ITEMS; q += V)
+                *reinterpret_cast<typename Vec16<T>::type*>(g + e0 + q) =
+                    *reinterpret_cast<const typename Vec16<T>::type*>(v + q);
+        }
+    } else if (changed) {
+#pragma unroll
+        for (int q = 0; q < CP_ITEMS; ++q)
+            if (e0 + q < len) g[e0 + q] = v[q];
+    }
+}
+
+static inline bool per_row_fits(int64_t L) { return L / 4 < 0x7fffffff; }
+
+// ---- register-window fast path (window <= 9, vector-aligned rows) ---------------------------
+// The streaming kernels above stage a tile in shared memory and synchronise; for the small
+// windows the reference actually uses (3..9) that costs more than it saves.  Here every thread
+// produces G*V consecutive outputs (V = 16 bytes / element) straight from registers: it loads
+// its own G vectors plus HV neighbour vectors on each side with 16-byte loads (neighbour
+// vectors are L1 hits, their owners load them too), evaluates the window with fully unrolled
+// register indexing, and writes 16-byte vectors.  No shared memory, no barrier, 8 loads in
+// flight per thread.
+template <typename T, int MODE /*0 pad value, 1 edge*/>
+__device__ __forceinline__ void load_window_vec(const T* __restrict__ src, const int64_t len, const int64_t e0,
+                                                const T padv, T* w) {
+    constexpr int V = Vec16<T>::V;
+    if (e0 >= 0 && e0 + V <= len) {
+        const typename Vec16<T>::type v = __ldg(reinterpret_cast<const typename Vec16<T>::type*>(src + e0));
+        const T* pv = reinterpret_cast<const T*>(&v);
+#pragma unroll
+        for (int c = 0; c < V; ++c) w[c] = pv[c];
+    } else {
+#pragma unroll
+        for (int c = 0; c < V; ++c) {
+            const int64_t g = e0 + c;
+            if (MODE == 1) w[c] = src[g < 0 ? 0 : (g >= len ? len - 1 : g)];
+            else w[c] = (g >= 0 && g < len) ? src[g] : padv;
+        }
+    }
+}
+
+template <typename T, int H, bool CONV>
+__global__ void __launch_bounds__(256) temporal_window_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                              int64_t L, int64_t ld,
+                                                              const int32_t* __restrict__ lengths,
+                                                              int groups_per_row, T padv,
+                                                              const T* __restrict__ taps, int n_channels,
+                                                              int pad_mode) {
+    constexpr int V = Vec16<T>::V;
+    constexpr int G = 2;                       // own vectors per thread
+    constexpr int HV = (H + V - 1) / V;        // neighbour vectors per side
+    constexpr int NW = (G + 2 * HV) * V;       // window elements held in registers
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t row = gid / groups_per_row;
+    const int64_t grp = gid - row * groups_per_row;
+    const int64_t len = lengths ? (int64_t)lengths[row] : L;
+    const int64_t o0 = grp * (G * V);          // first output element of this thread
+    if (o0 >= len) return;
+    const T* src = in + row * ld;
+    T win[NW];
+#pragma unroll
+    for (int v = 0; v < G + 2 * HV; ++v) {
+        const int64_t e0 = o0 + (int64_t)(v - HV) * V;
+        if (CONV && pad_mode == VDET_PAD_EDGE) load_window_vec<T, 1>(src, len, e0, padv, win + v * V);
+        else load_window_vec<T, 0>(src, len, e0, padv, win + v * V);
+    }
+    T tap[2 * H + 1];
+    if (CONV) {
+        const T* tp = taps + (row % n_channels) * (2 * H + 1);
+#pragma unroll
+        for (int k = 0; k < 2 * H + 1; ++k) tap[k] = __ldg(tp + k);
+    }
+    T res[G * V];
+#pragma unroll
+    for (int o = 0; o < G * V; ++o) {
+        const int c = HV * V + o;              // centre of the window in win[]
+        if (CONV) {
+            T acc = (T)0;
+#pragma unroll
+            for (int k = 0; k < 2 * H + 1; ++k) acc = t_add(acc, t_mul(tap[k], win[c - H + k]));
+            res[o] = acc;
+        } else {
+            T m = win[c - H];
+#pragma unroll
+            for (int k = 1; k < 2 * H + 1; ++k) m = t_max(m, win[c - H + k]);
+            res[o] = m;
+        }
+    }
+    T* dst = out + row * ld + o0;
+#pragma unroll
+    for (int v = 0; v < G; ++v) {
+        if (o0 + (v + 1) * V <= len) {
+            *reinterpret_cast<typename Vec16<T>::type*>(dst + v * V) =
+                *reinterpret_cast<const typename Vec16<T>::type*>(res + v * V);
+        } else {
+#pragma unroll
+            for (int c = 0; c < V; ++c)
+                if (o0 + v * V + c < len) dst[v * V + c] = res[v * V + c];
+        }
+    }
+}
+
+template <typename T, bool CONV>
+static int run_window_fast(const void* in, void* out, int64_t n_rows, int64_t L, int64_t ld, const int32_t* lengths,
+                           int h, double pad, const void* taps, int n_channels, int pad_mode, cudaStream_t st) {
+    constexpr int V = Vec16<T>::V;
+    const int64_t per_row = (L + 2 * V - 1) / (2 * V);
+    const int64_t total = per_row * n_rows;
+    const int64_t grid = (total + 255) / 256;
+    if (grid > 0x7fffffff) { set_error("temporal: grid too large"); return VDET_ERR_UNSUPPORTED; }
+#define VDET_WIN_LAUNCH(HH) temporal_window_kernel<T, HH, CONV><<<(unsigned)grid, 256, 0, st>>>( \
+        (const T*)in, (T*)out, L, ld, lengths, (int)per_row, (T)pad, (const T*)taps, n_channels, pad_mode)
+    switch (h) {
+        case 1: VDET_WIN_LAUNCH(1); break;
+        case 2: VDET_WIN_LAUNCH(2); break;
+        case 3: VDET_WIN_LAUNCH(3); break;
+        default: VDET_WIN_LAUNCH(4); break;
+    }
+#undef VDET_WIN_LAUNCH
+    VDET_LAUNCH_CHECK();
+    return VDET_OK;
+}
+
+template <typename T>
+static bool window_fast_ok(const void* in, const void* out, int64_t ld, int64_t L, int window) {
+    constexpr int V = Vec16<T>::V;
+    return window >= 3 && window <= 9 && (ld % V) == 0 && L < 0x7fffffff && per_row_fits(L) &&
+           ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0;
 }
 
 template <typename T>
 static int run_maxpool(const void* in, void* out, int64_t n_rows, int64_t L, int64_t ld, const int32_t* lengths,
                        int window, double pad, cudaStream_t st) {
     const int h = window / 2;
+    if (window_fast_ok<T>(in, out, ld, L, window))
+        return run_window_fast<T, false>(in, out, n_rows, L, ld, lengths, h, pad, nullptr, 1, 0, st);
     const size_t smem = (size_t)(TP_TILE + 2 * h) * sizeof(T);
     if (smem > max_dynamic_smem(temporal_maxpool_kernel<T>)) { set_error("temporal_maxpool: window %d too large", window); return VDET_ERR_UNSUPPORTED; }
     VDET_CUDA(allow_dynamic_smem(temporal_maxpool_kernel<T>, smem));
@@ -203,6 +427,8 @@ template <typename T>
 static int run_conv(const void* in, void* out, int64_t n_rows, int64_t L, int64_t ld, const int32_t* lengths,
                     const void* taps, int n_channels, int window, int pad_mode, cudaStream_t st) {
     const int h = window / 2;
+    if (window_fast_ok<T>(in, out, ld, L, window) && ((uintptr_t)taps & (sizeof(T) - 1)) == 0)
+        return run_window_fast<T, true>(in, out, n_rows, L, ld, lengths, h, 0.0, taps, n_channels, pad_mode, st);
     const size_t smem = (size_t)(TP_TILE + 2 * h + window) * sizeof(T);
     if (smem > max_dynamic_smem(temporal_conv1d_kernel<T>)) { set_error("temporal_conv1d: window %d too large", window); return VDET_ERR_UNSUPPORTED; }
     VDET_CUDA(allow_dynamic_smem(temporal_conv1d_kernel<T>, smem));
@@ -218,18 +444,22 @@ static int run_conv(const void* in, void* out, int64_t n_rows, int64_t L, int64_
 
 template <typename T>
 static int run_completion(void* scores, int64_t n_rows, int64_t L, int64_t ld, const int32_t* lengths,
-                          double miss_thr, uint32_t* status, cudaStream_t st) {
-    const int cap = (int)((L + 3) / 4 * 4);
-    const size_t smem = (size_t)cap * (sizeof(T) + 2 * sizeof(int32_t));
-    if (smem > max_dynamic_smem(score_completion_kernel<T>)) {
-        set_error("score_completion: rows of %lld elements exceed the shared-memory row limit of this build",
-                  (long long)L);
-        return VDET_ERR_UNSUPPORTED;
+                          double miss_thr, uint32_t* status, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const int64_t tiles = (L + CP_TILE - 1) / CP_TILE;
+    const int64_t n_tiles = tiles * n_rows;
+    if (n_tiles > 0x7fffffff || L >= 0x7fffffff) { set_error("score_completion: too large"); return VDET_ERR_UNSUPPORTED; }
+    const size_t need = (size_t)n_tiles * sizeof(TileBounds<T>);
+    if (ws == nullptr || ws_bytes < need) {
+        set_error("score_completion: workspace of %zu bytes needed", need);
+        return VDET_ERR_WORKSPACE;
     }
-    VDET_CUDA(allow_dynamic_smem(score_completion_kernel<T>, smem));
-    if (n_rows > 0x7fffffff) { set_error("score_completion: too many rows"); return VDET_ERR_UNSUPPORTED; }
-    score_completion_kernel<T><<<(unsigned)n_rows, CP_THREADS, smem, st>>>((T*)scores, L, ld, lengths, (T)miss_thr,
-                                                                           cap, status);
+    TileBounds<T>* bounds = (TileBounds<T>*)ws;
+    completion_bounds_kernel<T><<<(unsigned)((n_tiles + 7) / 8), 256, 0, st>>>((const T*)scores, L, ld, lengths,
+                                                                              (int)tiles, n_tiles, (T)miss_thr, bounds);
+    VDET_LAUNCH_CHECK();
+    const int vec_ok = (((uintptr_t)scores & 15) == 0 && (ld % (16 / sizeof(T))) == 0) ? 1 : 0;
+    completion_fill_kernel<T><<<(unsigned)n_tiles, CP_THREADS, 0, st>>>((T*)scores, L, ld, lengths, (int)tiles,
+                                                                         (T)miss_thr, vec_ok, bounds, status);
     VDET_LAUNCH_CHECK();
     return VDET_OK;
 }
@@ -238,15 +468,22 @@ static int run_completion(void* scores, int64_t n_rows, int64_t L, int64_t ld, c
 
 using namespace vdet;
 
+extern "C" size_t vdet_score_completion_workspace_bytes(int64_t n_rows, int64_t L, int dtype) {
+    const int64_t tiles = (L + CP_TILE - 1) / CP_TILE;
+    const size_t rec = dtype == VDET_DTYPE_F64 ? sizeof(TileBounds<double>) : sizeof(TileBounds<float>);
+    return (size_t)(tiles * (n_rows > 0 ? n_rows : 0)) * rec + 256;
+}
+
 extern "C" int vdet_score_completion(void* scores, int dtype, int64_t n_rows, int64_t L, int64_t ld,
-                                     const int32_t* lengths, double miss_thr, uint32_t* status, void* stream) {
+                                     const int32_t* lengths, double miss_thr, uint32_t* status,
+                                     void* ws, size_t ws_bytes, void* stream) {
     VDET_REQUIRE(n_rows >= 0 && L >= 0 && ld >= L, "score_completion: bad shape");
     VDET_REQUIRE(dtype == VDET_DTYPE_F32 || dtype == VDET_DTYPE_F64, "score_completion: bad dtype");
     VDET_REQUIRE(status != nullptr, "score_completion: null status");
     if (n_rows == 0 || L == 0) return VDET_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    return dtype == VDET_DTYPE_F32 ? run_completion<float>(scores, n_rows, L, ld, lengths, miss_thr, status, st)
-                                   : run_completion<double>(scores, n_rows, L, ld, lengths, miss_thr, status, st);
+    return dtype == VDET_DTYPE_F32 ? run_completion<float>(scores, n_rows, L, ld, lengths, miss_thr, status, ws, ws_bytes, st)
+                                   : run_completion<double>(scores, n_rows, L, ld, lengths, miss_thr, status, ws, ws_bytes, st);
 }
 
 extern "C" int vdet_temporal_maxpool(const void* scores, void* out, int dtype, int64_t n_rows, int64_t L,
@@ -254,6 +491,7 @@ extern "C" int vdet_temporal_maxpool(const void* scores, void* out, int dtype, i
     VDET_REQUIRE(n_rows >= 0 && L >= 0 && ld >= L, "temporal_maxpool: bad shape");
     VDET_REQUIRE(dtype == VDET_DTYPE_F32 || dtype == VDET_DTYPE_F64, "temporal_maxpool: bad dtype");
     VDET_REQUIRE(window >= 1 && (window % 2) == 1, "Window size must be odd!");     // tubelet_cls.py:389-390
+    VDET_REQUIRE(scores != out, "temporal_maxpool: out must not alias the input");
     if (n_rows == 0 || L == 0) return VDET_OK;
     cudaStream_t st = (cudaStream_t)stream;
     return dtype == VDET_DTYPE_F32 ? run_maxpool<float>(scores, out, n_rows, L, ld, lengths, window, pad, st)
@@ -267,6 +505,7 @@ extern "C" int vdet_temporal_conv1d(const void* x, void* out, int dtype, int64_t
     VDET_REQUIRE(dtype == VDET_DTYPE_F32 || dtype == VDET_DTYPE_F64, "temporal_conv1d: bad dtype");
     VDET_REQUIRE(window >= 1 && (window % 2) == 1, "temporal_conv1d: window must be odd");
     VDET_REQUIRE(pad_mode == VDET_PAD_ZERO || pad_mode == VDET_PAD_EDGE, "temporal_conv1d: bad pad mode");
+    VDET_REQUIRE(x != out, "temporal_conv1d: out must not alias the input");
     if (n_rows == 0 || L == 0) return VDET_OK;
     cudaStream_t st = (cudaStream_t)stream;
     return dtype == VDET_DTYPE_F32

@@ -302,8 +302,10 @@ def score_completion_(scores, lengths=None, miss_thr=-10.0, status=None):
     dt = _rows(scores, "scores")
     if status is None:
         status = new_status(scores.device)
+    ws_bytes = lib.vdet_score_completion_workspace_bytes(scores.shape[0], scores.shape[1], dt)
+    ws = _workspace(ws_bytes, scores.device)
     rc = lib.vdet_score_completion(_ptr(scores), dt, scores.shape[0], scores.shape[1], scores.stride(0),
-                                   _ptr(lengths), float(miss_thr), _ptr(status), _stream())
+                                   _ptr(lengths), float(miss_thr), _ptr(status), _ptr(ws), ws_bytes, _stream())
     _lib.check(rc, "score_completion")
     return status
 
