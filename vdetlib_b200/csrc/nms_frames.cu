@@ -158,9 +158,12 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 3 : 1)) nms_frames_
                 // contiguous [n, C] block: flat coalesced read, transposed conflict-free write
                 const float* src = p.scores + (int64_t)off * C;
                 const int total = n * C;
+                int r = tid / C, c = tid - r * C;                  // one division, then incremental
+                const int dr = NMS_THREADS / C, dc = NMS_THREADS - dr * C;
                 for (int f = tid; f < total; f += NMS_THREADS) {
-                    const int r = f / C, c = f - r * C;
                     sscore[c * SST + r] = __ldg(src + f);
+                    r += dr; c += dc;
+                    if (c >= C) { c -= C; ++r; }
                 }
             } else {
                 const int total = n * C;
@@ -316,7 +319,11 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 3 : 1)) nms_frames_
                 if (out_m && valid) out_m[i] = (uint8_t)mine;
                 cnt += __popc(kgrp);
             }
-            for (int e = cnt + lane; e < n; e += 32) out_idx[e] = -1;
+#pragma unroll 4
+            for (int g = cnt >> 5; g < Wn; ++g) {                 // -1 padding of the frame's unused slots
+                const int e = g * 32 + lane;
+                if (e >= cnt && e < n) out_idx[e] = -1;
+            }
             if (lane == 0) p.keep_cnt[p.frame_major ? ((int64_t)seg * C + c) : ((int64_t)c * p.n_segs + seg)] = cnt;
             __syncwarp();
         }

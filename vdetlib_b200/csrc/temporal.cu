@@ -134,7 +134,7 @@ template <> struct Vec16<double> { typedef double2 type; static constexpr int V 
 //          valid index" and min-scan of "next valid index" (warp shuffles + one shared-memory
 //          hop), closed form per missing element, 16-byte stores.
 constexpr int CP_THREADS = 256;
-constexpr int CP_ITEMS = 4;
+constexpr int CP_ITEMS = 8;
 constexpr int CP_TILE = CP_THREADS * CP_ITEMS;
 
 template <typename T>
