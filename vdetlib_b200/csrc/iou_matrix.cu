@@ -38,6 +38,9 @@ __device__ __forceinline__ void iou_matrix_f32_body(const float4* __restrict__ a
         col[k] = VEC ? (c0 + 4 * tid + k) : (c0 + warp * 128 + k * 32 + lane);
         bb[k] = col[k] < nb ? __ldg(b + col[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
         ba[k] = area_f32(bb[k]);
+        // keep the area in its register: without this nvcc rematerialises it (4 FADD + 1 FMUL)
+        // inside the row loop -- seen as 8.3 instead of 6 FADD per IoU in the first ncu capture
+        asm volatile("" : "+f"(ba[k]));
     }
     if (tid < IOU_TILE_R) {
         const int64_t r = r0 + tid;
@@ -47,6 +50,24 @@ __device__ __forceinline__ void iou_matrix_f32_body(const float4* __restrict__ a
     }
     __syncthreads();
     const int rows = (int)((na - r0) < IOU_TILE_R ? (na - r0) : IOU_TILE_R);
+    if (VEC && rows == IOU_TILE_R && c0 + IOU_TILE_C <= nb) {
+        // interior tile: no bounds checks, one 16-byte streaming store per thread and row
+        float* row = out + r0 * nb + c0 + 4 * tid;
+#pragma unroll 4
+        for (int r = 0; r < IOU_TILE_R; ++r, row += nb) {
+            const float4 av = s_a[r];
+            const float aa = s_aa[r];
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float inter, uni;
+                inter_union_f32(av, aa, bb[k], ba[k], inter, uni);
+                v[k] = FAST ? div_sane(inter, uni) : iou_quotient(inter, uni);
+            }
+            __stcs(reinterpret_cast<float4*>(row), make_float4(v[0], v[1], v[2], v[3]));
+        }
+        return;
+    }
 #pragma unroll 2
     for (int r = 0; r < rows; ++r) {
         const float4 av = s_a[r];
@@ -54,13 +75,9 @@ __device__ __forceinline__ void iou_matrix_f32_body(const float4* __restrict__ a
         float v[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if (FAST) {
-                float inter, uni;
-                inter_union_f32(av, aa, bb[k], ba[k], inter, uni);
-                v[k] = div_sane(inter, uni);
-            } else {
-                v[k] = pair_iou_f32(av, aa, bb[k], ba[k]);
-            }
+            float inter, uni;
+            inter_union_f32(av, aa, bb[k], ba[k], inter, uni);
+            v[k] = FAST ? div_sane(inter, uni) : iou_quotient(inter, uni);
         }
         float* row = out + (r0 + r) * nb;
         if (VEC) {
