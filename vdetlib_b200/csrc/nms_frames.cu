@@ -357,30 +357,64 @@ static int launch_nms_frames(const NmsFramesParams& p, size_t smem, int grid, cu
 // Big-frame variant: 1024 < max frame length <= 2048 (BASELINE config 5: 2000 boxes/frame).
 // Same three phases; what changes is where things live:
 //   * the bit matrix (N x N/32 words = 500 KB at N=2000) does not fit in shared memory: every
-//     persistent CTA owns a slot in a global scratch buffer, written with 32-byte-per-lane
-//     vector stores in phase B and read back (from L2) one 128/256-byte row per kept box;
-//   * the per-class sort runs per warp over a 64-bit key array in shared memory (bitonic,
-//     __syncwarp between steps) instead of registers;
-//   * the removed / kept sets take two words per lane.
+//     persistent CTA owns a slot in a global scratch buffer (L2 resident).  Phase B walks
+//     256x256 "super tiles" of the upper triangle: warp w evaluates row block w of the super
+//     tile against its 8 column blocks (same filtered, division-free mask_tile as the small
+//     kernel), stores its own 8 words with two 16-byte stores, and the transposed words --
+//     collected from ballots -- go through a shared staging tile so that the mirrored rows are
+//     also written with 32-byte row segments instead of scattered words;
+//   * the per-class order is built per warp in shared memory: bitonic sort of the 32-bit score
+//     keys, rank by binary search, and -- only when scores tie -- a stable ordinal among equal
+//     keys from match.any ballots over the elements in index order (the radix-sort ranking trick),
+//     which reproduces "descending score, then ascending row" without a 64-bit network;
+//   * the removed set takes two words per lane; mask rows are read from the CTA's global slot.
 // ==========================================================================================
 constexpr int BIG_MAX = 2048;
+constexpr int BIG_ST_LD = 9;     // padded row of the transposed staging tile (8 words + 1)
+
+__device__ __noinline__ void zero_division_check_big(const uint32_t* ord, int n, const float4* sbox,
+                                                     const float* sarea, uint32_t rem0, uint32_t rem1, uint32_t ci,
+                                                     int pos, int lane, uint32_t* status) {
+    const float4 bi = sbox[ci];
+    const float ai = sarea[ci];
+    bool zd = false;
+    for (int base = pos + 1; base < n; base += 32) {             // warp-uniform trip count
+        const int k2 = base + lane;
+        const bool act = k2 < n;
+        const uint32_t j = act ? ord[k2] : 0u;
+        const uint32_t w0 = __shfl_sync(FULL, rem0, (int)((j >> 5) & 31));
+        const uint32_t w1 = __shfl_sync(FULL, rem1, (int)((j >> 5) & 31));
+        const uint32_t wj = ((j >> 5) & 32) ? w1 : w0;
+        if (act && !((wj >> (j & 31)) & 1u)) {
+            float inter, uni;
+            inter_union_f32(bi, ai, sbox[j], sarea[j], inter, uni);
+            zd |= (uni == 0.0f);
+        }
+    }
+    if (__any_sync(FULL, zd) && lane == 0) atomicOr(status, VDET_STATUS_ZERO_DIVISION);
+}
 
 __global__ void __launch_bounds__(NMS_THREADS) nms_frames_big_kernel(const NmsFramesParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int NB = p.nb;            // multiple of 256 here (8 column words per tile)
+    const int NB = p.nb;            // multiple of 256
     const int W = NB >> 5;          // <= 64
     const int NPAD = p.npad;
     float4* sbox = reinterpret_cast<float4*>(smem_raw);
     float* sarea = reinterpret_cast<float*>(sbox + NB);
     int32_t* srow = reinterpret_cast<int32_t*>(sarea + NB);
-    uint64_t* skeys = reinterpret_cast<uint64_t*>(srow + NB);      // [NMS_WARPS][NPAD]
+    uint32_t* sT = reinterpret_cast<uint32_t*>(srow + NB);                  // [256][BIG_ST_LD]
+    uint32_t* skeys = sT + 256 * BIG_ST_LD;                                 // [NMS_WARPS][NPAD] keys, then order
+    uint16_t* srank = reinterpret_cast<uint16_t*>(skeys + NMS_WARPS * NPAD);  // [NMS_WARPS][NPAD]
+    uint16_t* scnt = srank + NMS_WARPS * NPAD;                              // [NMS_WARPS][NPAD] tie counters
     __shared__ int s_zero_union;
     uint32_t* gmask = p.gmask + (size_t)blockIdx.x * NB * W;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C = p.n_classes;
     const float T = p.thresh_f32;
-    uint64_t* keys = skeys + (size_t)warp * NPAD;
+    uint32_t* sk = skeys + (size_t)warp * NPAD;
+    uint16_t* rk = srank + (size_t)warp * NPAD;
+    uint16_t* ct = scnt + (size_t)warp * NPAD;
 
     for (int seg = blockIdx.x; seg < p.n_segs; seg += gridDim.x) {
         const int off = p.seg_offsets[seg];
@@ -402,120 +436,165 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_frames_big_kernel(const NmsFr
             srow[e] = row;
         }
         __syncthreads();
-        // ---- B: bit matrix into this CTA's global slot; tile = 32 rows x 8 words -----------
+        const int Wn = (n + 31) >> 5;
+        // ---- B: bit matrix, 256x256 super tiles of the upper triangle ------------------------
         {
-            const int Wn = (n + 31) >> 5;
-            const int G = (Wn + 7) >> 3;                 // groups of 8 column words
-            const int ntiles = Wn * G;
-            for (int tile = warp; tile < ntiles; tile += NMS_WARPS) {
-                const int rb = tile / G, g = tile - rb * G;
-                const int i = rb * 32 + lane;
-                const float4 bi = sbox[i];
-                const float ai = sarea[i];
-                uint32_t words[8];
-                bool zero = false;
+            const int SBn = (n + 255) >> 8;
+            for (int R = 0; R < SBn; ++R) {
+                for (int Cc = R; Cc < SBn; ++Cc) {
+                    const int rb = R * 8 + warp;
+                    const int i = rb * 32 + lane;
+                    if (rb < Wn) {
+                        const float4 bi = sbox[i];
+                        const float ai = sarea[i];
+                        uint32_t words[8];
+                        bool any_zero = false;
+#pragma unroll 1
+                        for (int cbl = 0; cbl < 8; ++cbl) {
+                            const int cb = Cc * 8 + cbl;
+                            uint32_t word = 0, tword = 0;
+                            if (cb < Wn) {
+                                bool zero, unc;
+                                if (p.fast_filter) {
+                                    word = mask_tile<true>(bi, ai, sbox, sarea, cb, T, lane, tword, zero, unc);
+                                    if (__any_sync(FULL, unc))
+                                        word = mask_tile<false>(bi, ai, sbox, sarea, cb, T, lane, tword, zero, unc);
+                                } else {
+                                    word = mask_tile<false>(bi, ai, sbox, sarea, cb, T, lane, tword, zero, unc);
+                                }
+                                any_zero |= zero;
+                                const int cvalid = n - cb * 32, rvalid = n - rb * 32;
+                                if (cvalid < 32) word &= (1u << cvalid) - 1u;
+                                if (rvalid < 32) tword &= (1u << rvalid) - 1u;
+                            }
+                            // dynamic register index avoided: select into the 8 words
 #pragma unroll
-                for (int cw = 0; cw < 8; ++cw) {
-                    const int cb = g * 8 + cw;
-                    uint32_t word = 0;
-                    if (cb < Wn) {
-#pragma unroll 8
-                        for (int jj = 0; jj < 32; ++jj) {
-                            const int j = cb * 32 + jj;
-                            float inter, uni;
-                            inter_union_f32(bi, ai, sbox[j], sarea[j], inter, uni);
-                            if (iou_ge(inter, uni, T)) word |= (1u << jj);
-                            zero |= (uni == 0.0f) && (i != j) && (i < n) && (j < n);
+                            for (int q = 0; q < 8; ++q)
+                                if (q == cbl) words[q] = word;
+                            if (Cc > R) sT[(cbl * 32 + lane) * BIG_ST_LD + warp] = tword;
                         }
-                        const int valid = n - cb * 32;
-                        if (valid < 32) word &= (valid <= 0) ? 0u : ((1u << valid) - 1u);
+                        uint4* dst = reinterpret_cast<uint4*>(gmask + (size_t)i * W + Cc * 8);
+                        dst[0] = make_uint4(words[0], words[1], words[2], words[3]);
+                        dst[1] = make_uint4(words[4], words[5], words[6], words[7]);
+                        if (__any_sync(FULL, any_zero) && lane == 0) s_zero_union = 1;
+                    } else if (Cc > R) {
+                        for (int cbl = 0; cbl < 8; ++cbl) sT[(cbl * 32 + lane) * BIG_ST_LD + warp] = 0u;
                     }
-                    words[cw] = word;
+                    if (Cc > R) {                    // mirrored rows: 32-byte row segments from the staging tile
+                        __syncthreads();
+                        const int j = Cc * 256 + tid;
+                        if (j < NB) {
+                            const uint32_t* src = sT + tid * BIG_ST_LD;
+                            uint4* dst = reinterpret_cast<uint4*>(gmask + (size_t)j * W + R * 8);
+                            dst[0] = make_uint4(src[0], src[1], src[2], src[3]);
+                            dst[1] = make_uint4(src[4], src[5], src[6], src[7]);
+                        }
+                        __syncthreads();
+                    }
                 }
-                uint4* dst = reinterpret_cast<uint4*>(gmask + (size_t)i * W + g * 8);
-                dst[0] = make_uint4(words[0], words[1], words[2], words[3]);
-                dst[1] = make_uint4(words[4], words[5], words[6], words[7]);
-                if (__any_sync(FULL, zero) && lane == 0) s_zero_union = 1;
             }
         }
         __syncthreads();      // block-scope visibility of this CTA's own global writes
         const bool check_zero = (s_zero_union != 0);
-        const int Wn = (n + 31) >> 5;
 
         for (int c = warp; c < C; c += NMS_WARPS) {
-            for (int e = lane; e < NPAD; e += 32) {
-                uint64_t k = ~0ull;
-                if (e < n) {
-                    const float s = __ldg(p.scores + (int64_t)srow[e] * p.score_ldr + (int64_t)c * p.score_ldc);
-                    k = ((uint64_t)f32_key_desc(s) << 32) | (uint32_t)e;
-                }
-                keys[e] = k;
-            }
+            const float* sc_glob = p.scores + (int64_t)c * p.score_ldc;
+            auto score_key = [&](const int e) -> uint32_t {
+                return f32_key_desc(__ldg(sc_glob + (int64_t)srow[e] * p.score_ldr));
+            };
+            // -- keys, sorted ascending in shared memory (= descending score)
+            for (int e = lane; e < NPAD; e += 32) sk[e] = e < n ? score_key(e) : 0xffffffffu;
             __syncwarp();
             for (int size = 2; size <= NPAD; size <<= 1) {
                 for (int stride = size >> 1; stride > 0; stride >>= 1) {
                     for (int t = lane; t < (NPAD >> 1); t += 32) {
                         const int i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
                         const int j = i + stride;
-                        const uint64_t a = keys[i], b = keys[j];
+                        const uint32_t a = sk[i], b = sk[j];
                         const bool up = (i & size) == 0;
-                        if (up ? (a > b) : (a < b)) { keys[i] = b; keys[j] = a; }
+                        sk[i] = up ? min(a, b) : max(a, b);
+                        sk[j] = up ? max(a, b) : min(a, b);
                     }
                     __syncwarp();
                 }
             }
-            uint32_t rem0 = 0, rem1 = 0, kept0 = 0, kept1 = 0;
+            // -- ties?  (equal adjacent keys among the n valid entries)
+            bool tie = false;
+            for (int q = lane; q + 1 < n; q += 32) tie |= (sk[q] == sk[q + 1]);
+            const bool has_tie = __any_sync(FULL, tie);
+            if (has_tie) {
+                for (int e = lane; e < n; e += 32) ct[e] = 0;
+                __syncwarp();
+            }
+            // -- rank of every element: lower bound of its key (+ stable ordinal among equal keys)
+            for (int base = 0; base < n; base += 32) {
+                const int e = base + lane;
+                const bool act = e < n;
+                const uint32_t key = act ? score_key(e) : 0xffffffffu;
+                uint32_t pos = 0;
+                for (int step = NPAD >> 1; step > 0; step >>= 1) {
+                    const uint32_t q = pos + step - 1;
+                    if (q < (uint32_t)n && sk[q] < key) pos += step;
+                }
+                if (has_tie) {
+                    // elements arrive in index order: the ordinal among equal keys is the running count
+                    // of that key (kept at its lower-bound slot) plus the lanes below me with the same key
+                    const unsigned peers = __match_any_sync(FULL, act ? key : (0xfffffff0u ^ (uint32_t)lane));
+                    const int leader = __ffs(peers) - 1;
+                    uint32_t old = 0;
+                    if (act && lane == leader) { old = ct[pos]; ct[pos] = (uint16_t)(old + __popc(peers)); }
+                    old = __shfl_sync(FULL, old, leader);
+                    pos += old + __popc(peers & lanemask_lt());
+                    __syncwarp();
+                }
+                if (act) rk[e] = (uint16_t)pos;
+            }
+            __syncwarp();
+            // -- invert: sk becomes the order (index at each sorted position)
+            for (int e = lane; e < n; e += 32) sk[rk[e]] = (uint32_t)e;
+            __syncwarp();
+
+            uint32_t rem0 = 0, rem1 = 0;
             int cnt = 0;
-            int32_t buf = -1;
             const int64_t blk = p.frame_major ? ((int64_t)off * C + (int64_t)c * n) : ((int64_t)c * p.n_rows + off);
             int32_t* out_idx = p.keep_idx + blk;
-            for (int k = 0; k < n; ++k) {
-                const uint32_t i = (uint32_t)keys[k];                       // broadcast read
-                const uint32_t w = i >> 5;
-                const uint32_t word = __shfl_sync(FULL, (w & 32) ? rem1 : rem0, (int)(w & 31));
-                if ((word >> (i & 31)) & 1u) continue;                      // warp-uniform
-                if (check_zero) {
-                    const float4 bi = sbox[i];
-                    const float ai = sarea[i];
-                    bool zd = false;
-                    for (int base = k + 1; base < n; base += 32) {            // warp-uniform trip count
-                        const int k2 = base + lane;
-                        const bool act = k2 < n;
-                        const uint32_t j = act ? (uint32_t)keys[k2] : 0u;
-                        // every lane needs the removed word of its own j: fetch both halves
-                        const uint32_t w0 = __shfl_sync(FULL, rem0, (int)((j >> 5) & 31));
-                        const uint32_t w1 = __shfl_sync(FULL, rem1, (int)((j >> 5) & 31));
-                        const uint32_t wj = ((j >> 5) & 32) ? w1 : w0;
-                        if (act && !((wj >> (j & 31)) & 1u)) {
-                            float inter, uni;
-                            inter_union_f32(bi, ai, sbox[j], sarea[j], inter, uni);
-                            zd |= (uni == 0.0f);
-                        }
-                    }
-                    if (__any_sync(FULL, zd) && lane == 0) atomicOr(p.status, VDET_STATUS_ZERO_DIVISION);
+            uint8_t* out_m = p.keep_mask ? p.keep_mask + blk : nullptr;
+            const unsigned lt = lanemask_lt();
+#pragma unroll 1
+            for (int g = 0; g < Wn; ++g) {
+                const bool valid = (g * 32 + lane) < n;
+                const uint32_t i = valid ? sk[g * 32 + lane] : 0u;
+                const int src = (int)((i >> 5) & 31);
+                const bool hi = ((i >> 5) & 32) != 0;
+                const uint32_t w0 = __shfl_sync(FULL, rem0, src), w1 = __shfl_sync(FULL, rem1, src);
+                unsigned alive = __ballot_sync(FULL, valid && !(((hi ? w1 : w0) >> (i & 31)) & 1u));
+                unsigned kgrp = 0;
+                while (alive) {
+                    const int l = __ffs(alive) - 1;
+                    const uint32_t ci = __shfl_sync(FULL, i, l);
+                    if (check_zero)
+                        zero_division_check_big(sk, n, sbox, sarea, rem0, rem1, ci, g * 32 + l, lane, p.status);
+                    const uint32_t* row = gmask + (size_t)ci * W;
+                    const uint32_t r0 = (lane < Wn) ? row[lane] : 0u;
+                    const uint32_t r1 = (32 + lane < Wn) ? row[32 + lane] : 0u;
+                    rem0 |= r0;
+                    rem1 |= r1;
+                    kgrp |= (1u << l);
+                    const uint32_t v0 = __shfl_sync(FULL, r0, src), v1 = __shfl_sync(FULL, r1, src);
+                    alive &= ~__ballot_sync(FULL, ((hi ? v1 : v0) >> (i & 31)) & 1u);
+                    alive &= ~(1u << l);
                 }
-                const uint32_t* row = gmask + (size_t)i * W;
-                if (lane < Wn) rem0 |= row[lane];
-                if (32 + lane < Wn) rem1 |= row[32 + lane];
-                if (lane == (int)(w & 31)) { if (w & 32) kept1 |= (1u << (i & 31)); else kept0 |= (1u << (i & 31)); }
-                if (lane == (cnt & 31)) buf = srow[i];
-                ++cnt;
-                if ((cnt & 31) == 0) out_idx[cnt - 32 + lane] = buf;
+                const bool mine = (kgrp >> lane) & 1u;
+                if (mine) out_idx[cnt + __popc(kgrp & lt)] = srow[i];
+                if (out_m && valid) out_m[i] = (uint8_t)mine;
+                cnt += __popc(kgrp);
             }
-            {
-                const int done = cnt & ~31;
-                if (done + lane < cnt) out_idx[done + lane] = buf;
-                for (int e = cnt + lane; e < n; e += 32) out_idx[e] = -1;
-                if (lane == 0) p.keep_cnt[p.frame_major ? ((int64_t)seg * C + c) : ((int64_t)c * p.n_segs + seg)] = cnt;
+#pragma unroll 4
+            for (int g = cnt >> 5; g < Wn; ++g) {
+                const int e = g * 32 + lane;
+                if (e >= cnt && e < n) out_idx[e] = -1;
             }
-            if (p.keep_mask) {
-                uint8_t* out_m = p.keep_mask + blk;
-                for (int wi = 0; wi < Wn; ++wi) {
-                    const uint32_t kw = __shfl_sync(FULL, (wi & 32) ? kept1 : kept0, wi & 31);
-                    const int e = wi * 32 + lane;
-                    if (e < n) out_m[e] = (uint8_t)((kw >> lane) & 1u);
-                }
-            }
+            if (lane == 0) p.keep_cnt[p.frame_major ? ((int64_t)seg * C + c) : ((int64_t)c * p.n_segs + seg)] = cnt;
             __syncwarp();
         }
         __syncthreads();
@@ -523,7 +602,8 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_frames_big_kernel(const NmsFr
 }
 
 static size_t big_smem_bytes(int nb, int npad) {
-    return (size_t)nb * (sizeof(float4) + sizeof(float) + sizeof(int32_t)) + (size_t)NMS_WARPS * npad * sizeof(uint64_t);
+    return (size_t)nb * (sizeof(float4) + sizeof(float) + sizeof(int32_t)) + 256 * BIG_ST_LD * sizeof(uint32_t) +
+           (size_t)NMS_WARPS * npad * (sizeof(uint32_t) + 2 * sizeof(uint16_t));
 }
 
 }  // namespace vdet
