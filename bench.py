@@ -197,9 +197,21 @@ def run_b200(args):
             return 2
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout = the one JSON line
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout must carry exactly one JSON line: NCCL prints its version banner to stdout when the
+        # environment sets NCCL_DEBUG, so file descriptor 1 points at stderr while the communicator
+        # is created (init + first collective) and is restored afterwards.
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     T, N, C = T_FRAMES, N_BOXES, N_CLASSES
     K, W = args.steps, max(args.warmup, 3)
 
