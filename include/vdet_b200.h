@@ -168,10 +168,12 @@ int vdet_iou_bitmask_f32(const float* boxes, int n, double thresh, uint32_t* mas
  * For every packed row p of frame s < S-1: succ[p] = packed row of the best box of frame
  * s+1 (or -1 if that frame is empty), best_iou[p] = its IoU.  Rows of the LAST frame are
  * linked against `halo_boxes` [n_halo,4] (the first frame of the next shard, from the
- * boundary allgather); succ is then the index INTO the halo, -1 when n_halo == 0.
+ * boundary allgather); succ is then halo_row_base + the index into the halo (-1 when n_halo == 0).
+ * halo_row_base lets a caller split one video into two calls (frames [0,k) with frame k as the
+ * halo and halo_row_base = its packed row offset) and still get packed-row successors.
  * ------------------------------------------------------------------------------------- */
 int vdet_link_frames_f32(const float* boxes, const int32_t* seg_offsets, int n_segs,
-                         int max_seg_len, const float* halo_boxes, int n_halo,
+                         int max_seg_len, const float* halo_boxes, int n_halo, int halo_row_base,
                          int32_t* succ, float* best_iou, int64_t n_rows, void* stream);
 
 /* ---------------------------------------------------------------------------------------

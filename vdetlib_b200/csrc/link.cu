@@ -20,7 +20,8 @@ constexpr int LINK_STAGE = 1024;     // boxes of frame t+1 staged per pass
 __global__ void __launch_bounds__(LINK_THREADS) link_frames_kernel(const float4* __restrict__ boxes,
                                                                    const int32_t* __restrict__ seg_offsets,
                                                                    int n_segs, const float4* __restrict__ halo,
-                                                                   int n_halo, int32_t* __restrict__ succ,
+                                                                   int n_halo, int halo_row_base,
+                                                                   int32_t* __restrict__ succ,
                                                                    float* __restrict__ best_iou) {
     __shared__ float4 s_box[LINK_STAGE];
     __shared__ float s_area[LINK_STAGE];
@@ -32,7 +33,7 @@ __global__ void __launch_bounds__(LINK_THREADS) link_frames_kernel(const float4*
     const bool last = (seg == n_segs - 1);
     const float4* nxt = last ? halo : boxes + seg_offsets[seg + 1];
     const int m = last ? n_halo : (seg_offsets[seg + 2] - seg_offsets[seg + 1]);
-    const int out_base = last ? 0 : seg_offsets[seg + 1];
+    const int out_base = last ? halo_row_base : seg_offsets[seg + 1];
 
     const bool active = i < n;
     const float4 bi = active ? __ldg(boxes + off + i) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(LINK_THREADS) link_frames_kernel(const float4*
 using namespace vdet;
 
 extern "C" int vdet_link_frames_f32(const float* boxes, const int32_t* seg_offsets, int n_segs,
-                                    int max_seg_len, const float* halo_boxes, int n_halo,
+                                    int max_seg_len, const float* halo_boxes, int n_halo, int halo_row_base,
                                     int32_t* succ, float* best_iou, int64_t n_rows, void* stream) {
     VDET_REQUIRE(n_segs >= 0 && max_seg_len >= 0 && n_halo >= 0 && n_rows >= 0, "link_frames: negative size");
     if (n_segs == 0 || n_rows == 0 || max_seg_len == 0) return VDET_OK;
@@ -91,7 +92,7 @@ extern "C" int vdet_link_frames_f32(const float* boxes, const int32_t* seg_offse
     VDET_REQUIRE(max_seg_len <= 65535 * LINK_THREADS, "link_frames: frame too long");
     dim3 grid((unsigned)n_segs, (unsigned)((max_seg_len + LINK_THREADS - 1) / LINK_THREADS));
     link_frames_kernel<<<grid, LINK_THREADS, 0, (cudaStream_t)stream>>>(
-        (const float4*)boxes, seg_offsets, n_segs, (const float4*)halo_boxes, n_halo, succ, best_iou);
+        (const float4*)boxes, seg_offsets, n_segs, (const float4*)halo_boxes, n_halo, halo_row_base, succ, best_iou);
     VDET_LAUNCH_CHECK();
     return VDET_OK;
 }

@@ -40,6 +40,10 @@ struct NmsFramesParams {
     int fast_filter;   // 1: division-free threshold filter allowed (2^-20 <= T <= 2)
     int so_words;      // per-warp order scratch: (nb/32)*33 words
     int frame_major;   // output layout (VDET_LAYOUT_*)
+    // work items: frames [0, split_from) are one item each; every later frame is cut into `nsplit`
+    // class ranges (each item rebuilds the frame's bit matrix) so that the last, partially filled
+    // round of the persistent grid still occupies every CTA slot
+    int split_from, nsplit, n_items;
 };
 
 // One 32x32 tile of the suppression bit matrix: lane = row i (box in registers), the 32 columns
@@ -132,7 +136,15 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 3 : 1)) nms_frames_
     const int C = p.n_classes;
     const float T = p.thresh_f32;
 
-    for (int seg = blockIdx.x; seg < p.n_segs; seg += gridDim.x) {
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        int seg = item, c_begin = 0, c_end = C;
+        if (item >= p.split_from) {
+            const int q = item - p.split_from;
+            seg = p.split_from + q / p.nsplit;
+            const int part = q - (seg - p.split_from) * p.nsplit;
+            c_begin = (int)((int64_t)part * C / p.nsplit);
+            c_end = (int)((int64_t)(part + 1) * C / p.nsplit);
+        }
         const int off = p.seg_offsets[seg];
         const int n = p.seg_offsets[seg + 1] - off;
         if (n > NB) {   // caller's max_seg_len was wrong: refuse loudly instead of truncating
@@ -211,7 +223,7 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 3 : 1)) nms_frames_
         // ---- C: per class: order by score + greedy walk (one warp per class) ---------------
         uint32_t* so = sord + warp * p.so_words;          // this warp's order scratch (skewed)
         const int cap = Wn * 32;                          // sorted positions >= cap are padding
-        for (int c = warp; c < C; c += NMS_WARPS) {
+        for (int c = c_begin + warp; c < c_end; c += NMS_WARPS) {
             const float* sc_smem = sscore + c * SST;
             const float* sc_glob = p.scores + (int64_t)c * p.score_ldc;
             auto score_key = [&](const int e) -> uint32_t {
@@ -331,6 +343,21 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 3 : 1)) nms_frames_
     }
 }
 
+// Work items for a persistent grid of `slots` CTAs over n_segs frames (see NmsFramesParams).
+static void plan_items(NmsFramesParams& p, int slots) {
+    p.split_from = p.n_segs; p.nsplit = 1; p.n_items = p.n_segs;
+    if (slots <= 0 || p.n_classes < 2) return;
+    const int rem = p.n_segs % slots;
+    if (rem == 0 || rem * 2 > slots) return;               // last round already (more than half) full
+    int ns = slots / rem;
+    if (ns > p.n_classes) ns = p.n_classes;
+    if (ns > 8) ns = 8;
+    if (ns < 2) return;
+    p.split_from = p.n_segs - rem;
+    p.nsplit = ns;
+    p.n_items = p.split_from + rem * ns;
+}
+
 static size_t nms_smem_bytes(int nb, int nper, int n_classes, bool stage) {
     const int W = nb / 32, WS = W | 1;
     size_t b = (size_t)nb * (sizeof(float4) + sizeof(float) + sizeof(int32_t));
@@ -416,7 +443,15 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_frames_big_kernel(const NmsFr
     uint16_t* rk = srank + (size_t)warp * NPAD;
     uint16_t* ct = scnt + (size_t)warp * NPAD;
 
-    for (int seg = blockIdx.x; seg < p.n_segs; seg += gridDim.x) {
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        int seg = item, c_begin = 0, c_end = C;
+        if (item >= p.split_from) {
+            const int q = item - p.split_from;
+            seg = p.split_from + q / p.nsplit;
+            const int part = q - (seg - p.split_from) * p.nsplit;
+            c_begin = (int)((int64_t)part * C / p.nsplit);
+            c_end = (int)((int64_t)(part + 1) * C / p.nsplit);
+        }
         const int off = p.seg_offsets[seg];
         const int n = p.seg_offsets[seg + 1] - off;
         if (n > NB) {
@@ -497,7 +532,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_frames_big_kernel(const NmsFr
         __syncthreads();      // block-scope visibility of this CTA's own global writes
         const bool check_zero = (s_zero_union != 0);
 
-        for (int c = warp; c < C; c += NMS_WARPS) {
+        for (int c = c_begin + warp; c < c_end; c += NMS_WARPS) {
             const float* sc_glob = p.scores + (int64_t)c * p.score_ldc;
             auto score_key = [&](const int e) -> uint32_t {
                 return f32_key_desc(__ldg(sc_glob + (int64_t)srow[e] * p.score_ldr));
@@ -658,7 +693,8 @@ extern "C" int vdet_nms_frames_f32(const float* boxes, int box_ld,
         p.npad = BIG_MAX;
         p.stage = 0;
         int grid = sm_count_cached();
-        if (grid > n_segs) grid = n_segs;
+        plan_items(p, grid);
+        if (grid > p.n_items) grid = p.n_items;
         const size_t need = (size_t)grid * nb * (nb / 32) * sizeof(uint32_t);
         if (ws == nullptr || ws_bytes < need) {
             set_error("nms_frames: workspace of %zu bytes needed for %d-box frames", need, max_seg_len);
@@ -690,7 +726,8 @@ extern "C" int vdet_nms_frames_f32(const float* boxes, int box_ld,
     if (per_sm > 8) per_sm = 8;
     if (nper > 16) per_sm = 1; else if (per_sm > 3) per_sm = 3;      // register-limited residency
     int grid = sm_count_cached() * per_sm;
-    if (grid > n_segs) grid = n_segs;
+    plan_items(p, grid);
+    if (grid > p.n_items) grid = p.n_items;
     cudaStream_t st = (cudaStream_t)stream;
     switch (nper) {
         case 1:  return launch_nms_frames<1>(p, smem, grid, st);

@@ -81,15 +81,30 @@ class ShardedVideoPostProcessor(object):
         return halo
 
     def step_device(self, d_boxes, d_scores):
-        """Device-resident inputs; returns the result dict of VideoPostProcessor.run_device."""
+        """Device-resident inputs; returns the result dict of VideoPostProcessor.run_device.
+
+        The boundary all-gather is enqueued first on a side stream.  The persistent NMS grid fills
+        every SM, so the (tiny) NCCL kernel usually only gets in once NMS drains; to keep it off the
+        critical path the link is split: frames [0, T-1) are linked right after NMS with the local
+        frame T-1 as their halo, which overlaps the all-gather, and only the last frame waits for it.
+        """
         from . import ops
         pp = self.pp
+        T, N = pp.T, pp.N
         main = torch.cuda.current_stream()
-        halo = self._exchange(d_boxes[:self.n_boxes])          # overlaps the NMS kernel
-        out = ops.nms_frames(d_boxes, d_scores, pp.seg_offsets, pp.nms_thresh, pp.N, want_mask=True,
+        halo = self._exchange(d_boxes[:self.n_boxes])
+        out = ops.nms_frames(d_boxes, d_scores, pp.seg_offsets, pp.nms_thresh, N, want_mask=True,
                              status=pp.status, frame_major_out=True, out=(pp.d_idx, pp.d_cnt, pp.d_mask))
-        main.wait_stream(self.side)
-        succ, link_iou = ops.link_frames(d_boxes, pp.seg_offsets, pp.N, halo)
+        succ, link_iou = pp.d_succ, pp.d_iou
+        if self.exchange.world > 1 and T > 1:
+            last = (T - 1) * N
+            ops.link_frames(d_boxes[:last], pp.seg_offsets[:T], N, d_boxes[last:], halo_row_base=last,
+                            out=(succ[:last], link_iou[:last]))
+            main.wait_stream(self.side)
+            ops.link_frames(d_boxes[last:], pp.seg_offsets[:2], N, halo, out=(succ[last:], link_iou[last:]))
+        else:
+            main.wait_stream(self.side)
+            ops.link_frames(d_boxes, pp.seg_offsets, N, halo, out=(succ, link_iou))
         res = pp._views(out)
         res.update(succ=succ, link_iou=link_iou)
         return res

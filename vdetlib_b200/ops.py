@@ -238,23 +238,27 @@ def iou_bitmask(boxes, thresh, status=None):
     return mask, status
 
 
-def link_frames(boxes, seg_offsets, max_seg_len, halo=None):
+def link_frames(boxes, seg_offsets, max_seg_len, halo=None, halo_row_base=0, out=None):
     """Frame-to-frame link: for each box, the FIRST arg-max IoU box of the next frame.
-    Returns (succ i32 [n] packed row of the successor / halo index / -1, best_iou f32 [n])."""
+    Returns (succ i32 [n] packed row of the successor / halo_row_base + halo index / -1,
+    best_iou f32 [n]).  ``out=(succ, best_iou)`` writes into caller-provided buffers."""
     lib = _lib.load()
     _need(boxes, "boxes", torch.float32, 2)
     _need(seg_offsets, "seg_offsets", torch.int32, 1)
     boxes = boxes.contiguous()
     n = boxes.shape[0]
-    succ = torch.empty(n, dtype=torch.int32, device=boxes.device)
-    best = torch.empty(n, dtype=torch.float32, device=boxes.device)
+    if out is not None:
+        succ, best = out
+    else:
+        succ = torch.empty(n, dtype=torch.int32, device=boxes.device)
+        best = torch.empty(n, dtype=torch.float32, device=boxes.device)
     n_halo = 0
     if halo is not None:
         _need(halo, "halo", torch.float32, 2)
         halo = halo.contiguous()
         n_halo = halo.shape[0]
     rc = lib.vdet_link_frames_f32(_ptr(boxes), _ptr(seg_offsets), seg_offsets.numel() - 1, int(max_seg_len),
-                                  _ptr(halo), n_halo, _ptr(succ), _ptr(best), n, _stream())
+                                  _ptr(halo), n_halo, int(halo_row_base), _ptr(succ), _ptr(best), n, _stream())
     _lib.check(rc, "link_frames")
     return succ, best
 

@@ -91,6 +91,8 @@ class VideoPostProcessor(object):
         self.d_idx = torch.empty(rows * C, dtype=torch.int32, device=dev)
         self.d_mask = torch.empty(rows * C, dtype=torch.uint8, device=dev)
         self.d_cnt = torch.empty((T, C), dtype=torch.int32, device=dev)
+        self.d_succ = torch.empty(rows, dtype=torch.int32, device=dev)
+        self.d_iou = torch.empty(rows, dtype=torch.float32, device=dev)
         self.h_boxes = torch.empty((rows, 4), dtype=torch.float32).pin_memory()
         self.h_scores = torch.empty((rows, C), dtype=torch.float32).pin_memory()
         self.h_mask = torch.empty(rows * C, dtype=torch.uint8).pin_memory()
