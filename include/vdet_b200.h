@@ -64,6 +64,10 @@ int         vdet_abi_version(void);
 const char* vdet_last_error(void);
 /* Number of SMs of `device` (grid sizing for callers); <0 on error. */
 int         vdet_sm_count(int device);
+/* Persistent kernels (the NMS grid) normally occupy every SM.  A multi-GPU caller that overlaps a
+ * collective with them reserves a few SMs so that the collective's kernel can be scheduled at
+ * once instead of waiting for the persistent grid to drain (process-wide setting, default 0). */
+int         vdet_set_reserved_sms(int n);
 
 /* ---------------------------------------------------------------------------------------
  * Per-frame greedy NMS on class-shared boxes.

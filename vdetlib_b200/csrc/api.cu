@@ -37,6 +37,15 @@ int sm_count_cached() {
     return v > 0 ? v : 148;
 }
 
+static int g_reserved_sms = 0;
+
+int usable_sm_count() {
+    const int n = sm_count_cached() - g_reserved_sms;
+    return n > 0 ? n : 1;
+}
+
+void set_reserved_sms(int n) { g_reserved_sms = n < 0 ? 0 : n; }
+
 int max_optin_smem_cached() {
     static int cache[64];
     int v = attr_cached(cudaDevAttrMaxSharedMemoryPerBlockOptin, cache);
@@ -50,6 +59,11 @@ extern "C" {
 int vdet_abi_version(void) { return VDET_ABI_VERSION; }
 
 const char* vdet_last_error(void) { return vdet::g_err; }
+
+int vdet_set_reserved_sms(int n) {
+    vdet::set_reserved_sms(n);
+    return VDET_OK;
+}
 
 int vdet_sm_count(int device) {
     int v = 0;

@@ -347,8 +347,11 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 3 : 1)) nms_frames_
 static void plan_items(NmsFramesParams& p, int slots) {
     p.split_from = p.n_segs; p.nsplit = 1; p.n_items = p.n_segs;
     if (slots <= 0 || p.n_classes < 2) return;
-    const int rem = p.n_segs % slots;
-    if (rem == 0 || rem * 2 > slots) return;               // last round already (more than half) full
+    // Only launches that cannot fill the grid once are split (a single image with 30 classes, a short
+    // clip): measured on config 2, splitting the LAST round of a multi-round launch does not pay --
+    // the CTAs of a thin last round already run alone on their SMs and finish early.
+    if (p.n_segs * 2 > slots) return;
+    const int rem = p.n_segs;
     int ns = slots / rem;
     if (ns > p.n_classes) ns = p.n_classes;
     if (ns > 8) ns = 8;
@@ -649,7 +652,7 @@ extern "C" size_t vdet_nms_frames_workspace_bytes(int max_seg_len, int n_classes
     (void)n_classes; (void)device;
     if (max_seg_len <= 1024) return 256;   // register-sort variants keep everything in shared memory
     const size_t nb = ((size_t)max_seg_len + 255) / 256 * 256;
-    return (size_t)sm_count_cached() * nb * (nb / 32) * sizeof(uint32_t) + 256;
+    return (size_t)sm_count_cached() * nb * (nb / 32) * sizeof(uint32_t) + 256;   // upper bound: all SMs
 }
 
 extern "C" int vdet_nms_frames_f32(const float* boxes, int box_ld,
@@ -692,7 +695,7 @@ extern "C" int vdet_nms_frames_f32(const float* boxes, int box_ld,
         p.nb = nb;
         p.npad = BIG_MAX;
         p.stage = 0;
-        int grid = sm_count_cached();
+        int grid = usable_sm_count();
         plan_items(p, grid);
         if (grid > p.n_items) grid = p.n_items;
         const size_t need = (size_t)grid * nb * (nb / 32) * sizeof(uint32_t);
@@ -725,7 +728,7 @@ extern "C" int vdet_nms_frames_f32(const float* boxes, int box_ld,
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
     if (nper > 16) per_sm = 1; else if (per_sm > 3) per_sm = 3;      // register-limited residency
-    int grid = sm_count_cached() * per_sm;
+    int grid = usable_sm_count() * per_sm;
     plan_items(p, grid);
     if (grid > p.n_items) grid = p.n_items;
     cudaStream_t st = (cudaStream_t)stream;

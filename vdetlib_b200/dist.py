@@ -68,8 +68,11 @@ class ShardedVideoPostProcessor(object):
         from .vdet.video_det import VideoPostProcessor
         self.pp = VideoPostProcessor(n_frames, n_boxes, n_classes, nms_thresh, device, n_chunks=n_chunks)
         self.exchange = BoundaryExchange(n_boxes, self.pp.device, group)
-        self.side = torch.cuda.Stream(device=self.pp.device)
+        self.side = torch.cuda.Stream(device=self.pp.device, priority=-1)
         self.n_boxes = n_boxes
+        if self.exchange.world > 1:
+            from . import _lib
+            _lib.load().vdet_set_reserved_sms(2)       # room for the all-gather next to the NMS grid
 
     def _exchange(self, d_first_frame):
         """Boundary all-gather on the side stream; returns (halo, join) -- call join() before the link."""
@@ -83,28 +86,17 @@ class ShardedVideoPostProcessor(object):
     def step_device(self, d_boxes, d_scores):
         """Device-resident inputs; returns the result dict of VideoPostProcessor.run_device.
 
-        The boundary all-gather is enqueued first on a side stream.  The persistent NMS grid fills
-        every SM, so the (tiny) NCCL kernel usually only gets in once NMS drains; to keep it off the
-        critical path the link is split: frames [0, T-1) are linked right after NMS with the local
-        frame T-1 as their halo, which overlaps the all-gather, and only the last frame waits for it.
-        """
+        The boundary all-gather is enqueued first, on a side stream, and overlaps the NMS kernel: with
+        more than one rank a few SMs are kept out of the persistent NMS grid (vdet_set_reserved_sms)
+        so that the NCCL kernel is scheduled immediately; the link kernel then waits on it."""
         from . import ops
         pp = self.pp
-        T, N = pp.T, pp.N
         main = torch.cuda.current_stream()
         halo = self._exchange(d_boxes[:self.n_boxes])
-        out = ops.nms_frames(d_boxes, d_scores, pp.seg_offsets, pp.nms_thresh, N, want_mask=True,
+        out = ops.nms_frames(d_boxes, d_scores, pp.seg_offsets, pp.nms_thresh, pp.N, want_mask=True,
                              status=pp.status, frame_major_out=True, out=(pp.d_idx, pp.d_cnt, pp.d_mask))
-        succ, link_iou = pp.d_succ, pp.d_iou
-        if self.exchange.world > 1 and T > 1:
-            last = (T - 1) * N
-            ops.link_frames(d_boxes[:last], pp.seg_offsets[:T], N, d_boxes[last:], halo_row_base=last,
-                            out=(succ[:last], link_iou[:last]))
-            main.wait_stream(self.side)
-            ops.link_frames(d_boxes[last:], pp.seg_offsets[:2], N, halo, out=(succ[last:], link_iou[last:]))
-        else:
-            main.wait_stream(self.side)
-            ops.link_frames(d_boxes, pp.seg_offsets, N, halo, out=(succ, link_iou))
+        main.wait_stream(self.side)
+        succ, link_iou = ops.link_frames(d_boxes, pp.seg_offsets, pp.N, halo, out=(pp.d_succ, pp.d_iou))
         res = pp._views(out)
         res.update(succ=succ, link_iou=link_iou)
         return res
