@@ -229,6 +229,20 @@ int vdet_threshold_topk_f32(const float* scores, const int32_t* seg_offsets, int
                             int32_t* idx_out, int32_t* cnt_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Densify strided tubelets (score_proto_interpolation, vdet/tubelet_cls.py:430-490).
+ * Every tubelet has >= 2 knots (frames ascending).  knot_x [n_knots] frame ids as float64, knot_y
+ * [n_fields, n_knots] the fields to interpolate, knot_off [n_tubelets+1]; the dense frames of
+ * tubelet k are dense_first[k] + 0,1,... occupying out columns [dense_off[k], dense_off[k+1]);
+ * dense_tub [n_dense] = tubelet of each dense column.  out [n_fields, n_dense] float64.  Linear
+ * interpolation as numpy.interp inside the knots, linear extrapolation (extrap1d) outside.
+ * ------------------------------------------------------------------------------------- */
+int vdet_tubelet_interpolate_f64(const double* knot_x, const double* knot_y, int64_t n_knots,
+                                 const int32_t* knot_off, const int32_t* dense_off,
+                                 const int32_t* dense_first, const int32_t* dense_tub,
+                                 int n_tubelets, int n_fields, int64_t n_dense, double* out,
+                                 void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Stable sort of (score, id) pairs by DESCENDING score (equal scores keep their input order).
  * The merge step of a frame-sharded vid_nms: every rank all-gathers its kept (score, global row)
  * list and sorts the concatenation into the reference's global keep order (utils/nms.pyx:80,97).

@@ -155,6 +155,25 @@ def main():
     protos["out"]["greedy_raw"] = R.greedily_track_from_raw_dets(vid, det_info, fake_tracker, 3, opts)
     # image nms
     protos["out"]["image_nms"] = R.apply_image_nms(boxes[0].astype(np.float64), scores[0, :, 0].astype(np.float64), 0.4)
+    # ---- 6. score_proto_interpolation on strided tubelets ---------------------
+    rng = np.random.default_rng(4100)
+    vid40 = synth.vid_proto(40)
+    tubs = []
+    for k, frames in enumerate([list(range(2, 39, 3)), list(range(5, 40, 5)), [7], list(range(1, 41, 4)),
+                                [3, 4, 9, 10, 30], list(range(2, 40, 2))]):
+        bxs = []
+        x1, y1 = float(rng.uniform(0, 500)), float(rng.uniform(0, 300))
+        for q, fr in enumerate(frames):
+            bb = [x1 + 3.5 * q, y1 + 1.25 * q, x1 + 3.5 * q + 80.0, y1 + 1.25 * q + 60.0]
+            if k % 2 == 0:
+                bb = [int(v) for v in bb]
+            bxs.append({'frame': fr, 'bbox': bb, 'det_score': float(rng.uniform(-1, 1)), 'anchor': fr - frames[len(frames) // 2],
+                        'track_score': 0.5, 'hash': 'h'})
+        tubs.append({'gt': 0, 'class': classes[3], 'class_index': 3, 'boxes': bxs})
+    sp_strided = {'video': vid40['video'], 'method': 'm', 'tubelets': tubs}
+    protos["interp_in"] = sp_strided
+    protos["interp_vid"] = vid40
+    protos["out"]["interp"] = R.score_proto_interpolation(copy.deepcopy(sp_strided), vid40)
     with open(os.path.join(OUT, "protos.json"), "w") as f:
         json.dump(protos, f, default=lambda o: o.tolist() if hasattr(o, "tolist") else float(o))
     print("golden vectors written to", OUT)

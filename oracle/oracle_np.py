@@ -397,3 +397,55 @@ def greedily_track_from_det(vid_proto, det_proto, track_method, score_fun, opts)
         tracks.extend(new_tracks)
         greedy_track_nms_step(det_info, keep, frame_to_det_ids, new_tracks, nms_thres)
     return {'video': vid_proto['video'], 'method': track_method.__name__, 'tracks': tracks}, keep
+
+
+def interp_value(xs, ys, x):
+    """One interpolated value as the reference computes it (vdet/tubelet_cls.py:416-428, :462-463):
+    numpy.interp's formula inside the knots (scipy interp1d kind='linear' delegates to it), the
+    extrap1d closed forms outside."""
+    xs = np.asarray(xs, dtype=np.float64)
+    ys = np.asarray(ys, dtype=np.float64)
+    x = np.float64(x)
+    if x < xs[0]:
+        return ys[0] + (x - xs[0]) * (ys[1] - ys[0]) / (xs[1] - xs[0])
+    if x > xs[-1]:
+        return ys[-1] + (x - xs[-1]) * (ys[-1] - ys[-2]) / (xs[-1] - xs[-2])
+    j = int(np.searchsorted(xs, x, side='right')) - 1
+    if j == len(xs) - 1 or xs[j] == x:
+        return ys[j]
+    slope = (ys[j + 1] - ys[j]) / (xs[j + 1] - xs[j])
+    return slope * (x - xs[j]) + ys[j]
+
+
+def score_proto_interpolation(score_proto, vid_proto):
+    """vdet/tubelet_cls.py:430-490."""
+    new = {'video': score_proto['video'], 'method': score_proto['method'] + '_interpolation', 'tubelets': []}
+    max_frames = len(vid_proto['frames'])
+    for tubelet in score_proto['tubelets']:
+        if tubelet['gt'] == 1:
+            raise ValueError('Dangerous: Score file contains gt tracks!')
+        if len(tubelet['boxes']) < 2:
+            new['tubelets'].append(copy.copy(tubelet))
+            continue
+        boxes = tubelet['boxes']
+        idx = np.asarray([b['frame'] for b in boxes])
+        order = np.argsort(idx, kind='mergesort')
+        xs = idx[order]
+        fields = {
+            'x1': [b['bbox'][0] for b in boxes], 'y1': [b['bbox'][1] for b in boxes],
+            'x2': [b['bbox'][2] for b in boxes], 'y2': [b['bbox'][3] for b in boxes],
+            'det_score': [b['det_score'] for b in boxes], 'anchor': [b['anchor'] for b in boxes]}
+        fields = {k: np.asarray(v, dtype=np.float64)[order] for k, v in fields.items()}
+        lo, hi = int(idx.min()), int(idx.max())
+        if lo == 2:
+            lo = 1
+        if hi == max_frames - 1:
+            hi = max_frames
+        out = {key: tubelet[key] for key in ['gt', 'class', 'class_index']}
+        out['boxes'] = []
+        for d in range(lo, hi + 1):
+            v = {k: float(interp_value(xs, fields[k], d)) for k in fields}
+            out['boxes'].append({'frame': d, 'det_score': v['det_score'], 'anchor': v['anchor'],
+                                 'bbox': [v['x1'], v['y1'], v['x2'], v['y2']]})
+        new['tubelets'].append(out)
+    return new

@@ -209,3 +209,25 @@ def test_threshold_topk_vs_oracle():
         want = oracle_np.threshold_topk_frame(scores[t], boxes[t], 0.05, 100)
         for j in range(1, C):
             assert np.array_equal(got[j][t], want[j]), (t, j)
+
+
+def test_score_proto_interpolation_golden():
+    p = helpers.golden_protos()
+    sp_in = copy.deepcopy(p["interp_in"])
+    got = tubelet_cls.score_proto_interpolation(sp_in, p["interp_vid"])
+    assert got == p["out"]["interp"]
+    assert sp_in == p["interp_in"]                                   # input untouched
+    spg = copy.deepcopy(p["interp_in"]); spg['tubelets'][1]['gt'] = 1
+    with pytest.raises(ValueError):
+        tubelet_cls.score_proto_interpolation(spg, p["interp_vid"])
+    # random strided tubelets vs the NumPy restatement
+    rng = np.random.default_rng(77)
+    tubs = []
+    for k in range(40):
+        frames = np.sort(rng.choice(np.arange(1, 201), size=int(rng.integers(2, 60)), replace=False)).tolist()
+        tubs.append({'gt': 0, 'class': CLASSES[2], 'class_index': 2, 'boxes': [
+            {'frame': fr, 'bbox': rng.uniform(0, 700, 4).tolist(), 'det_score': float(rng.normal()), 'anchor': fr - frames[0]}
+            for fr in frames]})
+    sp = {'video': 'v', 'method': 'm', 'tubelets': tubs}
+    vid = synth.vid_proto(200)
+    assert tubelet_cls.score_proto_interpolation(copy.deepcopy(sp), vid) == oracle_np.score_proto_interpolation(copy.deepcopy(sp), vid)

@@ -186,3 +186,11 @@ def test_np_oracle_vs_reference_live(ref_py):
             out = ref_py.score_proto_temporal_maxpool(copy.deepcopy(sp), w)
             assert np.array_equal(oracle_np.temporal_maxpool_row(ref_done, w),
                                   np.asarray(helpers.tubelet_scores(out)[0]))
+
+
+def test_np_oracle_interpolation_golden():
+    p = helpers.golden_protos()
+    got = oracle_np.score_proto_interpolation(copy.deepcopy(p["interp_in"]), p["interp_vid"])
+    assert got == p["out"]["interp"]
+    lens = [len(t['boxes']) for t in got['tubelets']]
+    assert lens[2] == 1 and lens[0] == 38 and lens[5] == 38        # single box kept; ends stretched (:472-475)

@@ -363,6 +363,26 @@ def threshold_topk(scores, seg_offsets, max_seg_len, thresh=0.05, k=100):
     return idx, cnt
 
 
+def tubelet_interpolate(knot_x, knot_y, knot_off, dense_first, dense_off):
+    """score_proto_interpolation's arithmetic for all tubelets at once (vdet/tubelet_cls.py:430-490).
+    knot_x f64 [n], knot_y f64 [F, n], knot_off / dense_off i32 [K+1], dense_first i32 [K].
+    Returns out f64 [F, n_dense]."""
+    lib = _lib.load()
+    _need(knot_x, "knot_x", torch.float64, 1)
+    _need(knot_y, "knot_y", torch.float64, 2)
+    knot_x, knot_y = knot_x.contiguous(), knot_y.contiguous()
+    K = knot_off.numel() - 1
+    n_dense = int(dense_off[-1].item()) if K > 0 else 0
+    counts = (dense_off[1:] - dense_off[:-1]).long()
+    dense_tub = torch.repeat_interleave(torch.arange(K, dtype=torch.int32, device=knot_x.device), counts)
+    out = torch.empty((knot_y.shape[0], n_dense), dtype=torch.float64, device=knot_x.device)
+    rc = lib.vdet_tubelet_interpolate_f64(_ptr(knot_x), _ptr(knot_y), knot_x.numel(), _ptr(knot_off), _ptr(dense_off),
+                                          _ptr(dense_first), _ptr(dense_tub), K, knot_y.shape[0], n_dense, _ptr(out),
+                                          _stream())
+    _lib.check(rc, "tubelet_interpolate")
+    return out
+
+
 def sort_by_score_desc(scores, ids):
     """Stable sort of (score f32, id i64) pairs by descending score (ties keep input order)."""
     lib = _lib.load()

@@ -283,3 +283,65 @@ def anchor_propagate(vid_proto, track_proto, det_proto, class_idx):
                 box['det_score'] = anchor_score
     score_proto['tubelets'] = tubelets_proto
     return score_proto
+
+
+# --------------------------------------------------------------------------------------
+# interpolation of strided tubelets
+# --------------------------------------------------------------------------------------
+_INTERP_FIELDS = ('x1', 'y1', 'x2', 'y2', 'det_score', 'anchor')
+
+
+def score_proto_interpolation(score_proto, vid_proto):
+    """Perform interpolation on score protocols if only part of the tracks are available.
+    vdet/tubelet_cls.py:430-490: every tubelet with >= 2 boxes is densified over
+    [min frame, max frame] (stretched to frame 1 / the last frame when it starts at 2 / ends one
+    before the end, :472-475) by linear interpolation of bbox, det_score and anchor; linear
+    extrapolation beyond the ends.  ValueError for gt tubelets (:447-448)."""
+    new_score_proto = {}
+    new_score_proto['video'] = score_proto['video']
+    new_score_proto['method'] = score_proto['method'] + '_interpolation'
+    max_frames = len(vid_proto['frames'])
+    tubelets_proto = [None] * len(score_proto['tubelets'])
+    todo = []
+    for t_i, tubelet in enumerate(score_proto['tubelets']):
+        if tubelet['gt'] == 1:
+            raise ValueError('Dangerous: Score file contains gt tracks!')
+        if len(tubelet['boxes']) < 2:
+            tubelets_proto[t_i] = copy.copy(tubelet)
+            continue
+        todo.append(t_i)
+    if todo:
+        xs, ys, knot_off, dense_first, dense_off = [], [[] for _ in _INTERP_FIELDS], [0], [], [0]
+        for t_i in todo:
+            boxes = score_proto['tubelets'][t_i]['boxes']
+            idx = np.asarray([b['frame'] for b in boxes])
+            order = np.argsort(idx, kind='mergesort')          # interp1d sorts its x (assume_sorted=False)
+            vals = [[b['bbox'][0] for b in boxes], [b['bbox'][1] for b in boxes], [b['bbox'][2] for b in boxes],
+                    [b['bbox'][3] for b in boxes], [b['det_score'] for b in boxes], [b['anchor'] for b in boxes]]
+            xs.extend(idx[order].tolist())
+            for f in range(6):
+                ys[f].extend(np.asarray(vals[f], dtype=np.float64)[order].tolist())
+            knot_off.append(len(xs))
+            min_idx, max_idx = int(idx.min()), int(idx.max())
+            if min_idx == 2:
+                min_idx = 1
+            if max_idx == max_frames - 1:
+                max_idx = max_frames
+            dense_first.append(min_idx)
+            dense_off.append(dense_off[-1] + max_idx - min_idx + 1)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        out = ops.tubelet_interpolate(
+            torch.tensor(xs, dtype=torch.float64, device=dev), torch.tensor(ys, dtype=torch.float64, device=dev),
+            torch.tensor(knot_off, dtype=torch.int32, device=dev), torch.tensor(dense_first, dtype=torch.int32, device=dev),
+            torch.tensor(dense_off, dtype=torch.int32, device=dev)).cpu().numpy()
+        for k, t_i in enumerate(todo):
+            tubelet = score_proto['tubelets'][t_i]
+            new_tubelet = {key: tubelet[key] for key in ['gt', 'class', 'class_index']}
+            cols = out[:, dense_off[k]:dense_off[k + 1]]
+            new_tubelet['boxes'] = [
+                {'frame': dense_first[k] + q, 'det_score': float(cols[4, q]), 'anchor': float(cols[5, q]),
+                 'bbox': [float(cols[0, q]), float(cols[1, q]), float(cols[2, q]), float(cols[3, q])]}
+                for q in range(cols.shape[1])]
+            tubelets_proto[t_i] = new_tubelet
+    new_score_proto['tubelets'] = tubelets_proto
+    return new_score_proto
