@@ -48,6 +48,7 @@ extern "C" {
 
 #define VDET_POOL_ARGMAX_SCORE 0      /* dets_spatial_max_pooling, tubelet_cls.py:334-340    */
 #define VDET_POOL_ARGMAX_IOU   1      /* anchor_propagate, tubelet_cls.py:375-377            */
+#define VDET_POOL_MAX_IOU      2      /* tubelets_overlap, utils/protocol.py:467-489: out_score = max IoU */
 
 #define VDET_PAD_ZERO 0
 #define VDET_PAD_EDGE 1
@@ -142,11 +143,14 @@ int vdet_track_nms_step_f32(const float* det_info, int64_t m,
  * SYNCHRONOUS (returns counts through host pointers).
  *   frames       pointer to the frame value of row 0, row stride `ld` floats
  *   row_valid    optional [n] uint8: rows with 0 are dropped
+ *   scores       optional (row stride scores_ld): rows inside a frame are then ordered by DESCENDING
+ *                score, ties by ascending row (frame_top_detections, utils/protocol.py:341-351)
  *   row_ids_out  [n] int32 packed row -> original row (ascending inside a frame)
  *   seg_offsets_out [n+1] int32 (first *n_segs_host+1 entries valid)
  *   seg_frame_out   optional [n] float32: frame value of each segment                    */
 size_t vdet_segment_workspace_bytes(int64_t n);
 int vdet_segment_by_frame(const float* frames, int ld, int64_t n, const uint8_t* row_valid,
+                          const float* scores, int scores_ld,
                           int32_t* row_ids_out, int32_t* seg_offsets_out, float* seg_frame_out,
                           int32_t* n_segs_host, int32_t* max_seg_len_host, int64_t* n_packed_host,
                           void* ws, size_t ws_bytes, void* stream);

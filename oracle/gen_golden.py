@@ -174,6 +174,31 @@ def main():
     protos["interp_in"] = sp_strided
     protos["interp_vid"] = vid40
     protos["out"]["interp"] = R.score_proto_interpolation(copy.deepcopy(sp_strided), vid40)
+    # ---- 7. tubelets_overlap / merge_score_protos / top detections ----------
+    annot = {'video': vid['video'], 'annotations': []}
+    smp = protos["out"]["smp_3"]
+    for k, tub in enumerate(smp['tubelets'][:4]):
+        tr = []
+        for q, bx in enumerate(tub['boxes']):
+            if bx['frame'] > T:
+                continue
+            bb = list(bx['bbox']) if k == 0 else [bx['bbox'][0] + 3 * k, bx['bbox'][1] - 2 * k, bx['bbox'][2] + k, bx['bbox'][3] + 5]
+            tr.append({'frame': bx['frame'], 'bbox': bb, 'class_index': 3 if (k < 3 or q < 2) else 7, 'class': 'c',
+                       'name': 'n', 'generated': False, 'occluded': False})
+        annot['annotations'].append({'id': str(k), 'track': tr})
+    annot['annotations'].append({'id': 'other', 'track': [{'frame': 1, 'bbox': [0, 0, 50, 50], 'class_index': 9}]})
+    protos["annot"] = annot
+    tubs_in = copy.deepcopy(smp['tubelets'])
+    tubs_in[0]['boxes'] = [b for b in tubs_in[0]['boxes'] if b['frame'] <= T]      # this one coincides with annotation 0
+    protos["overlap_in"] = copy.deepcopy(tubs_in)
+    protos["out"]["overlap"] = R.tubelets_overlap(tubs_in, annot, 3)
+    p1, p2 = copy.deepcopy(protos["out"]["smp_1"]), copy.deepcopy(protos["out"]["smp_1_05"])
+    protos["out"]["merge_max"] = R.merge_score_protos(p1, p2, scheme='max')
+    p1, p2 = copy.deepcopy(protos["out"]["smp_1"]), copy.deepcopy(protos["out"]["smp_3"])
+    protos["out"]["merge_combine"] = R.merge_score_protos(p1, p2, scheme='combine')
+    protos["out"]["top_50"] = [d['hash'] for d in R.top_detections(copy.deepcopy(det), 50, 2)['detections']]
+    protos["out"]["top_all"] = [d['hash'] for d in R.top_detections(copy.deepcopy(det), 100000, 2)['detections']]
+    protos["out"]["frame_top_5"] = [d['hash'] for d in R.frame_top_detections(copy.deepcopy(det), 5, 4)['detections']]
     with open(os.path.join(OUT, "protos.json"), "w") as f:
         json.dump(protos, f, default=lambda o: o.tolist() if hasattr(o, "tolist") else float(o))
     print("golden vectors written to", OUT)

@@ -449,3 +449,41 @@ def score_proto_interpolation(score_proto, vid_proto):
                                  'bbox': [v['x1'], v['y1'], v['x2'], v['y2']]})
         new['tubelets'].append(out)
     return new
+
+
+def tubelets_overlap(tubelets_proto, annot_proto, class_idx):
+    """utils/protocol.py:467-489 (in place)."""
+    for tubelet in tubelets_proto:
+        c = tubelet['class_index']
+        for tb in tubelet['boxes']:
+            tb['gt_overlap'] = 0
+            for annot_track in annot_proto['annotations']:
+                for ab in annot_track['track']:
+                    if ab['class_index'] != c:
+                        break
+                    if tb['frame'] == ab['frame']:
+                        cur = float(iou([ab['bbox']], [tb['bbox']]).ravel()[0])
+                        if cur > tb['gt_overlap']:
+                            tb['gt_overlap'] = cur
+        mean_iou = np.asarray([b['gt_overlap'] for b in tubelet['boxes']]).mean()
+        if abs(mean_iou - 1) < np.finfo(float).eps:
+            tubelet['gt'] = 1
+    return tubelets_proto
+
+
+def top_detections(det_proto, top_num, class_index):
+    """utils/protocol.py:330-339."""
+    if len(det_proto['detections']) < top_num:
+        return copy.copy(det_proto)
+    ranked = sorted(copy.copy(det_proto['detections']), key=lambda x: det_score(x, class_index), reverse=True)
+    return {'video': det_proto['video'], 'detections': ranked[:top_num]}
+
+
+def frame_top_detections(det_proto, top_num, class_index):
+    """utils/protocol.py:341-351."""
+    out = {'video': det_proto['video'], 'detections': []}
+    for frame_id in list(set([d['frame'] for d in det_proto['detections']])):
+        cur = sorted([d for d in det_proto['detections'] if d['frame'] == frame_id],
+                     key=lambda x: det_score(x, class_index), reverse=True)
+        out['detections'].extend(cur[:top_num])
+    return out

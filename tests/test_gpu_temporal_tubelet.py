@@ -231,3 +231,17 @@ def test_score_proto_interpolation_golden():
     sp = {'video': 'v', 'method': 'm', 'tubelets': tubs}
     vid = synth.vid_proto(200)
     assert tubelet_cls.score_proto_interpolation(copy.deepcopy(sp), vid) == oracle_np.score_proto_interpolation(copy.deepcopy(sp), vid)
+
+
+def test_overlap_merge_top_golden():
+    from vdetlib_b200.utils import protocol
+    p = helpers.golden_protos()
+    got = protocol.tubelets_overlap(copy.deepcopy(p["overlap_in"]), p["annot"], 3)
+    assert got == p["out"]["overlap"]
+    out = p["out"]
+    assert protocol.merge_score_protos(copy.deepcopy(out["smp_1"]), copy.deepcopy(out["smp_1_05"]), scheme='max') == out["merge_max"]
+    assert protocol.merge_score_protos(copy.deepcopy(out["smp_1"]), copy.deepcopy(out["smp_3"]), scheme='combine') == out["merge_combine"]
+    det = p["det"]
+    assert [d['hash'] for d in protocol.top_detections(copy.deepcopy(det), 50, 2)['detections']] == out["top_50"]
+    assert [d['hash'] for d in protocol.top_detections(copy.deepcopy(det), 100000, 2)['detections']] == out["top_all"]
+    assert [d['hash'] for d in protocol.frame_top_detections(copy.deepcopy(det), 5, 4)['detections']] == out["frame_top_5"]

@@ -194,3 +194,13 @@ def test_np_oracle_interpolation_golden():
     assert got == p["out"]["interp"]
     lens = [len(t['boxes']) for t in got['tubelets']]
     assert lens[2] == 1 and lens[0] == 38 and lens[5] == 38        # single box kept; ends stretched (:472-475)
+
+
+def test_np_oracle_overlap_and_top_golden():
+    p = helpers.golden_protos()
+    got = oracle_np.tubelets_overlap(copy.deepcopy(p["overlap_in"]), p["annot"], 3)
+    assert got == p["out"]["overlap"]
+    assert got[0]['gt'] == 1 and all(t['gt'] == 0 for t in got[1:])
+    det = p["det"]
+    assert [d['hash'] for d in oracle_np.top_detections(copy.deepcopy(det), 50, 2)['detections']] == p["out"]["top_50"]
+    assert [d['hash'] for d in oracle_np.frame_top_detections(copy.deepcopy(det), 5, 4)['detections']] == p["out"]["frame_top_5"]

@@ -14,7 +14,7 @@ ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED = -1, -2, -3, -4
 STATUS_ZERO_DIVISION = 1
 STATUS_ALL_MISSING = 2
 DTYPE_F32, DTYPE_F64 = 0, 1
-POOL_ARGMAX_SCORE, POOL_ARGMAX_IOU = 0, 1
+POOL_ARGMAX_SCORE, POOL_ARGMAX_IOU, POOL_MAX_IOU = 0, 1, 2
 PAD_ZERO, PAD_EDGE = 0, 1
 LAYOUT_CLASS_MAJOR, LAYOUT_FRAME_MAJOR = 0, 1
 
@@ -36,7 +36,7 @@ SIGNATURES = {
     "vdet_track_det_nms_f32": (_i64, [_vp, _i64, _i32, _vp, _i64, _i32, _f64, _vp, _vp, _vp, _sz, _vp]),
     "vdet_track_nms_step_f32": (_i32, [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _f64, _vp, _vp, _vp]),
     "vdet_segment_workspace_bytes": (_sz, [_i64]),
-    "vdet_segment_by_frame": (_i32, [_vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "vdet_segment_by_frame": (_i32, [_vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "vdet_iou_matrix_f32": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "vdet_iou_matrix_f64": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "vdet_iou_bitmask_f32": (_i32, [_vp, _i32, _f64, _vp, _vp, _vp]),

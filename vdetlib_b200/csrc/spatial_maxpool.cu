@@ -70,9 +70,9 @@ __global__ void __launch_bounds__(256) spatial_maxpool_kernel(const BT* __restri
             out_score[p] = -1e5;
         } else {
             out_arg[p] = off + arg;
-            out_score[p] = (mode == VDET_POOL_ARGMAX_SCORE)
-                               ? best
-                               : (double)det_scores[(int64_t)(off + arg) * score_ld];
+            out_score[p] = (mode == VDET_POOL_ARGMAX_IOU)
+                               ? (double)det_scores[(int64_t)(off + arg) * score_ld]
+                               : best;          // ARGMAX_SCORE: the score; MAX_IOU: the IoU itself
         }
     }
 }
@@ -100,7 +100,8 @@ extern "C" int vdet_spatial_maxpool(const void* tub_boxes, const int32_t* tub_se
                                     double thresh, int mode,
                                     int32_t* out_arg, double* out_score, void* stream) {
     VDET_REQUIRE(p >= 0 && n_segs >= 0, "spatial_maxpool: negative size");
-    VDET_REQUIRE(mode == VDET_POOL_ARGMAX_SCORE || mode == VDET_POOL_ARGMAX_IOU, "spatial_maxpool: bad mode");
+    VDET_REQUIRE(mode == VDET_POOL_ARGMAX_SCORE || mode == VDET_POOL_ARGMAX_IOU || mode == VDET_POOL_MAX_IOU,
+                 "spatial_maxpool: bad mode");
     VDET_REQUIRE((box_dtype | 1) == 1 && (score_dtype | 1) == 1, "spatial_maxpool: bad dtype");
     if (p == 0) return VDET_OK;
     cudaStream_t st = (cudaStream_t)stream;

@@ -261,6 +261,7 @@ using namespace vdet;
 extern "C" size_t vdet_segment_workspace_bytes(int64_t n) { return seg_ws_bytes(n > 0 ? n : 1); }
 
 extern "C" int vdet_segment_by_frame(const float* frames, int ld, int64_t n, const uint8_t* row_valid,
+                                     const float* scores, int scores_ld,
                                      int32_t* row_ids_out, int32_t* seg_offsets_out, float* seg_frame_out,
                                      int32_t* n_segs_host, int32_t* max_seg_len_host, int64_t* n_packed_host,
                                      void* ws, size_t ws_bytes, void* stream) {
@@ -275,7 +276,7 @@ extern "C" int vdet_segment_by_frame(const float* frames, int ld, int64_t n, con
     WsCarver c(ws, ws_bytes);
     SegWs w;
     if (!carve_seg(c, n, w)) { set_error("segment_by_frame: workspace too small"); return VDET_ERR_WORKSPACE; }
-    int rc = segment_async(frames, ld, n, row_valid, row_ids_out, seg_offsets_out, seg_frame_out, w, st);
+    int rc = segment_async(frames, ld, n, row_valid, row_ids_out, seg_offsets_out, seg_frame_out, w, st, scores, scores_ld);
     if (rc != VDET_OK) return rc;
     SegCounters h;
     VDET_CUDA(cudaMemcpyAsync(&h, w.cnt, sizeof(h), cudaMemcpyDeviceToHost, st));

@@ -163,8 +163,9 @@ def track_det_nms(tracks, dets, thresh):
     return _nms_entry("vdet_track_det_nms_f32", dets, 6, thresh, tracks=tracks)
 
 
-def segment_by_frame(frames, row_valid=None):
-    """Stable grouping of rows by their float32 frame value.
+def segment_by_frame(frames, row_valid=None, scores=None):
+    """Stable grouping of rows by their float32 frame value (with ``scores``: rows of a frame in
+    descending score, ties by ascending row).
 
     frames: 1-D float32 CUDA view (any stride).  Returns (row_ids i32 [n_packed], seg_offsets
     i32 [S+1], seg_frame f32 [S], max_seg_len).  Synchronises.
@@ -181,7 +182,11 @@ def segment_by_frame(frames, row_valid=None):
     n_segs, max_len, n_packed = ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int64(0)
     if row_valid is not None:
         _need(row_valid, "row_valid", torch.uint8, 1)
-    rc = lib.vdet_segment_by_frame(_ptr(frames), ld, n, _ptr(row_valid), _ptr(row_ids), _ptr(seg_off),
+    sld = 0
+    if scores is not None:
+        _need(scores, "scores", torch.float32, 1)
+        sld = scores.stride(0) if n > 1 else 1
+    rc = lib.vdet_segment_by_frame(_ptr(frames), ld, n, _ptr(row_valid), _ptr(scores), sld, _ptr(row_ids), _ptr(seg_off),
                                    _ptr(seg_frame), ctypes.byref(n_segs), ctypes.byref(max_len),
                                    ctypes.byref(n_packed), _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, "segment_by_frame")

@@ -9,6 +9,8 @@ import gzip
 import json
 import os
 
+import numpy as np
+
 from ..vdet.dataset import imagenet_vdet_classes
 
 
@@ -49,23 +51,59 @@ def score_proto(class_names, scores):
             for idx, (name, sc) in enumerate(zip(class_names, scores))]
 
 
+def _class_scores(det_proto, class_index):
+    return np.asarray([det_score(d, class_index) for d in det_proto['detections']], dtype=np.float64)
+
+
 def top_detections(det_proto, top_num, class_index):
-    """utils/protocol.py:330-339."""
+    """The ``top_num`` highest-scoring detections of the video.  utils/protocol.py:330-339
+    (stable descending sort; fewer than top_num detections -> a shallow copy, unsorted, :331-332).
+    The ranking is a stable radix sort on the GPU."""
+    import torch
+    from .. import ops
     if len(det_proto['detections']) < top_num:
         return copy.copy(det_proto)
-    ranked = sorted(copy.copy(det_proto['detections']),
-                    key=lambda x: det_score(x, class_index), reverse=True)
-    return {'video': det_proto['video'], 'detections': ranked[:top_num]}
+    scores = _class_scores(det_proto, class_index)
+    s32 = scores.astype(np.float32)
+    if not np.array_equal(s32.astype(np.float64), scores):
+        # scores that are not float32-representable would change ties: rank on the host like the reference
+        order = sorted(range(len(scores)), key=lambda i: scores[i], reverse=True)
+    else:
+        ids = torch.arange(len(scores), dtype=torch.int64, device="cuda")
+        order = ops.sort_by_score_desc(torch.from_numpy(s32).cuda(), ids)[1].cpu().tolist()
+    dets = det_proto['detections']
+    return {'video': det_proto['video'], 'detections': [dets[i] for i in order[:top_num]]}
 
 
 def frame_top_detections(det_proto, top_num, class_index):
-    """utils/protocol.py:341-351."""
-    out = {'video': det_proto['video'], 'detections': []}
-    for frame_id in list(set(d['frame'] for d in det_proto['detections'])):
-        cur = sorted([d for d in det_proto['detections'] if d['frame'] == frame_id],
-                     key=lambda x: det_score(x, class_index), reverse=True)
-        out['detections'].extend(cur[:top_num])
-    return out
+    """The ``top_num`` best detections of every frame.  utils/protocol.py:341-351 (frames visited in
+    the iteration order of ``set(frames)`` like the reference, stable descending sort inside a frame)."""
+    import torch
+    from .. import ops
+    new_det = {'video': det_proto['video'], 'detections': []}
+    dets = det_proto['detections']
+    if not dets:
+        return new_det
+    frame_idx = list(set([d['frame'] for d in dets]))
+    scores = _class_scores(det_proto, class_index)
+    s32 = scores.astype(np.float32)
+    frames = np.asarray([d['frame'] for d in dets], dtype=np.float32)
+    exact = np.array_equal(s32.astype(np.float64), scores) and np.array_equal(frames, [d['frame'] for d in dets])
+    if exact:
+        row_ids, seg_off, seg_frame, _ = ops.segment_by_frame(torch.from_numpy(frames).cuda(), None,
+                                                               torch.from_numpy(s32).cuda())
+        row_ids, seg_off = row_ids.cpu().numpy(), seg_off.cpu().numpy()
+        seg_of = {float(f): s for s, f in enumerate(seg_frame.cpu().tolist())}
+    for frame_id in frame_idx:
+        if exact:
+            s = seg_of[float(np.float32(frame_id))]
+            ranked = row_ids[seg_off[s]:seg_off[s + 1]][:top_num]
+            new_det['detections'].extend(dets[i] for i in ranked)
+        else:
+            cur = sorted([d for d in dets if d['frame'] == frame_id],
+                         key=lambda x: det_score(x, class_index), reverse=True)
+            new_det['detections'].extend(cur[:top_num])
+    return new_det
 
 
 def tubelets_proto_from_tracks_proto(tracks_proto, class_index):
@@ -82,3 +120,70 @@ def tubelets_proto_from_tracks_proto(tracks_proto, class_index):
         tubelets.append({'gt': 0, 'class_index': class_index,
                          'class': imagenet_vdet_classes[class_index], 'boxes': boxes})
     return tubelets
+
+
+def tubelets_overlap(tubelets_proto, annot_proto, class_idx):
+    """Ground-truth overlap of every tubelet box (``gt_overlap``) and the ``gt`` flag of tubelets
+    that coincide with an annotation.  utils/protocol.py:467-489: for a tubelet of class c, the best
+    IoU against the same-frame boxes of annotation tracks whose boxes carry class c (a track is read
+    up to its first box of another class, :476-478); ``gt = 1`` when the mean IoU is 1 (:486-488).
+    IoU in float64 on the GPU; IN PLACE like the reference."""
+    import torch
+    from .. import _lib, ops
+    classes = sorted(set(t['class_index'] for t in tubelets_proto))
+    for c in classes:
+        frame_boxes = {}
+        for annot_track in annot_proto['annotations']:
+            for annot_box in annot_track['track']:
+                if annot_box['class_index'] != c:
+                    break
+                frame_boxes.setdefault(annot_box['frame'], []).append(annot_box['bbox'])
+        tubs = [t for t in tubelets_proto if t['class_index'] == c]
+        boxes = [b for t in tubs for b in t['boxes']]
+        if not boxes:
+            continue
+        frames = sorted(frame_boxes)
+        seg_of = {f: s for s, f in enumerate(frames)}
+        seg_off = np.zeros(len(frames) + 1, dtype=np.int32)
+        np.cumsum([len(frame_boxes[f]) for f in frames], out=seg_off[1:])
+        ann = (np.concatenate([np.asarray(frame_boxes[f], dtype=np.float64).reshape(-1, 4) for f in frames])
+               if frames else np.zeros((0, 4)))
+        tb = np.asarray([b['bbox'] for b in boxes], dtype=np.float64).reshape(-1, 4)
+        seg = np.asarray([seg_of.get(b['frame'], -1) for b in boxes], dtype=np.int32)
+        dummy = torch.zeros(max(len(ann), 1), dtype=torch.float64, device="cuda")
+        arg, best = ops.spatial_maxpool(torch.from_numpy(tb).cuda(), torch.from_numpy(seg).cuda(),
+                                        torch.from_numpy(ann).cuda(), dummy, torch.from_numpy(seg_off).cuda(),
+                                        0.0, _lib.POOL_MAX_IOU)
+        arg, best = arg.cpu().numpy(), best.cpu().numpy()
+        for b, a, v in zip(boxes, arg, best):
+            b['gt_overlap'] = float(v) if (a >= 0 and v > 0) else 0            # :472, :482-483
+    for tubelet in tubelets_proto:
+        ious = [box['gt_overlap'] for box in tubelet['boxes']]
+        mean_iou = np.asarray(ious).mean()
+        if abs(mean_iou - 1) < np.finfo(float).eps:
+            tubelet['gt'] = 1
+    return tubelets_proto
+
+
+def merge_score_protos(proto_1, proto_2, scheme='combine'):
+    """utils/protocol.py:504-525: 'combine' appends the tubelets of proto_2, 'max' keeps per box the
+    entry with the larger det_score (host-side dict logic; no arithmetic beyond one comparison)."""
+    assert scheme in ['combine', 'max']
+    assert proto_1['video'] == proto_2['video']
+    new_proto = copy.copy(proto_1)
+    if proto_1['method'] != proto_2['method']:
+        new_proto['method'] = '_'.join([proto_1['method'], proto_2['method']])
+    if scheme == 'combine':
+        new_proto['tubelets'].extend(copy.copy(proto_2['tubelets']))
+    elif scheme == 'max':
+        for tubelet1, tubelet2 in zip(new_proto['tubelets'], proto_2['tubelets']):
+            assert tubelet1['gt'] == tubelet2['gt']
+            assert tubelet1['class'] == tubelet2['class']
+            assert tubelet1['class_index'] == tubelet2['class_index']
+            for box1, box2 in zip(tubelet1['boxes'], tubelet2['boxes']):
+                assert box1['frame'] == box2['frame']
+                assert box1['anchor'] == box2['anchor']
+                if box1['det_score'] < box2['det_score']:
+                    for key in box1:
+                        box1[key] = copy.copy(box2[key])
+    return new_proto
