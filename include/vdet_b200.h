@@ -150,7 +150,7 @@ int vdet_track_nms_step_f32(const float* det_info, int64_t m,
  *   seg_frame_out   optional [n] float32: frame value of each segment                    */
 size_t vdet_segment_workspace_bytes(int64_t n);
 int vdet_segment_by_frame(const float* frames, int ld, int64_t n, const uint8_t* row_valid,
-                          const float* scores, int scores_ld,
+                          const void* scores, int scores_ld, int scores_dtype,
                           int32_t* row_ids_out, int32_t* seg_offsets_out, float* seg_frame_out,
                           int32_t* n_segs_host, int32_t* max_seg_len_host, int64_t* n_packed_host,
                           void* ws, size_t ws_bytes, void* stream);
@@ -249,12 +249,13 @@ int vdet_tubelet_interpolate_f64(const double* knot_x, const double* knot_y, int
 /* ---------------------------------------------------------------------------------------
  * Stable sort of (score, id) pairs by DESCENDING score (equal scores keep their input order).
  * The merge step of a frame-sharded vid_nms: every rank all-gathers its kept (score, global row)
- * list and sorts the concatenation into the reference's global keep order (utils/nms.pyx:80,97).
+ * list and sorts the concatenation into the reference's global keep order (utils/nms.pyx:80,97);
+ * also the ranking of top_detections (utils/protocol.py:330-339).  dtype F32 or F64 (Python floats).
  * ------------------------------------------------------------------------------------- */
 size_t vdet_sort_workspace_bytes(int64_t n);
-int vdet_sort_by_score_desc_f32(const float* scores, const int64_t* ids, int64_t n,
-                                float* scores_out, int64_t* ids_out,
-                                void* ws, size_t ws_bytes, void* stream);
+int vdet_sort_by_score_desc(const void* scores, int dtype, const int64_t* ids, int64_t n,
+                            void* scores_out, int64_t* ids_out,
+                            void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -267,3 +267,8 @@ def test_sort_by_score_desc():
         so, io = ops.sort_by_score_desc(torch.from_numpy(sc).cuda(), torch.from_numpy(ids).cuda())
         order = np.argsort(-sc, kind="stable")
         assert np.array_equal(so.cpu().numpy(), sc[order]) and np.array_equal(io.cpu().numpy(), ids[order])
+        # float64 keys (Python-float scores): values that collapse in float32 stay ordered
+        sd = sc.astype(np.float64) + rng.integers(-3, 4, n) * 1e-12
+        so, io = ops.sort_by_score_desc(torch.from_numpy(sd).cuda(), torch.from_numpy(ids).cuda())
+        order = np.argsort(-sd, kind="stable")
+        assert np.array_equal(so.cpu().numpy(), sd[order]) and np.array_equal(io.cpu().numpy(), ids[order])

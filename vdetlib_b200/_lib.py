@@ -36,7 +36,7 @@ SIGNATURES = {
     "vdet_track_det_nms_f32": (_i64, [_vp, _i64, _i32, _vp, _i64, _i32, _f64, _vp, _vp, _vp, _sz, _vp]),
     "vdet_track_nms_step_f32": (_i32, [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _f64, _vp, _vp, _vp]),
     "vdet_segment_workspace_bytes": (_sz, [_i64]),
-    "vdet_segment_by_frame": (_i32, [_vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "vdet_segment_by_frame": (_i32, [_vp, _i32, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "vdet_iou_matrix_f32": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "vdet_iou_matrix_f64": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "vdet_iou_bitmask_f32": (_i32, [_vp, _i32, _f64, _vp, _vp, _vp]),
@@ -49,7 +49,7 @@ SIGNATURES = {
     "vdet_temporal_conv1d": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _vp]),
     "vdet_tubelet_interpolate_f64": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp]),
     "vdet_sort_workspace_bytes": (_sz, [_i64]),
-    "vdet_sort_by_score_desc_f32": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "vdet_sort_by_score_desc": (_i32, [_vp, _i32, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "vdet_threshold_topk_f32": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _i32, _vp, _vp, _vp]),
 }
 

@@ -220,18 +220,66 @@ static size_t seg_ws_bytes(int64_t n) {
     return 4 * (size_t)(n + 1) * 4 + (radix_scratch_elems(n) + scan_scratch_elems(n)) * 4 + 8 * 256 + 64;
 }
 
+
+// ---- stable order of rows by DESCENDING score (ties: ascending row), float32 or float64 ------
+// float64 keys are 64 bits: an LSD pair of 32-bit sorts (low word first, then the high word).
+__device__ __forceinline__ uint64_t f64_key_desc(double s) {
+    s = __dadd_rn(s, 0.0);                                   // -0.0 -> +0.0
+    const uint64_t b = (uint64_t)__double_as_longlong(s);
+    const uint64_t asc = b ^ ((b >> 63) ? 0xffffffffffffffffull : 0x8000000000000000ull);
+    return ~asc;
+}
+
+__global__ void k_score_keys64_lo(const double* __restrict__ scores, int ld, int64_t n, uint32_t* __restrict__ keys,
+                                  uint32_t* __restrict__ vals) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    keys[p] = (uint32_t)f64_key_desc(scores[p * (int64_t)ld]);
+    vals[p] = (uint32_t)p;
+}
+
+__global__ void k_score_keys64_hi(const double* __restrict__ scores, int ld, int64_t n,
+                                  const uint32_t* __restrict__ vals, uint32_t* __restrict__ keys) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    keys[p] = (uint32_t)(f64_key_desc(scores[(int64_t)vals[p] * ld]) >> 32);
+}
+
+// On return `vals` (length n) holds the rows in descending-score order.  keys/keys_alt/vals_alt/radix
+// are scratch as in SegWs.
+static int order_by_score(const void* scores, int sld, int dtype, int64_t n, uint32_t* keys, uint32_t* vals,
+                          uint32_t* keys_alt, uint32_t* vals_alt, uint32_t* radix, cudaStream_t st) {
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    if (dtype == VDET_DTYPE_F32) {
+        k_score_keys<<<nb, 256, 0, st>>>((const float*)scores, sld, n, keys, vals);
+        VDET_LAUNCH_CHECK();
+        const int f = radix_sort_pairs(keys, vals, keys_alt, vals_alt, n, 0, 32, radix, st);
+        if (f != 0) { if (f > 0) set_error("sort: unexpected parity"); return f < 0 ? f : VDET_ERR_INVALID; }
+        return VDET_OK;
+    }
+    k_score_keys64_lo<<<nb, 256, 0, st>>>((const double*)scores, sld, n, keys, vals);
+    VDET_LAUNCH_CHECK();
+    int f = radix_sort_pairs(keys, vals, keys_alt, vals_alt, n, 0, 32, radix, st);
+    if (f != 0) { if (f > 0) set_error("sort: unexpected parity"); return f < 0 ? f : VDET_ERR_INVALID; }
+    k_score_keys64_hi<<<nb, 256, 0, st>>>((const double*)scores, sld, n, vals, keys);
+    VDET_LAUNCH_CHECK();
+    f = radix_sort_pairs(keys, vals, keys_alt, vals_alt, n, 0, 32, radix, st);
+    if (f != 0) { if (f > 0) set_error("sort: unexpected parity"); return f < 0 ? f : VDET_ERR_INVALID; }
+    return VDET_OK;
+}
+
 // Asynchronous part of vdet_segment_by_frame; counters stay on the device in w.cnt.
 // With `scores` != nullptr the rows are first put in descending-score order (stable), so that
 // after the stable sort by frame every segment is internally in descending score with ties
 // by ascending row -- the order the any-length path walks.
 static int segment_async(const float* frames, int ld, int64_t n, const uint8_t* row_valid,
                          int32_t* row_ids_out, int32_t* seg_offsets_out, float* seg_frame_out,
-                         SegWs& w, cudaStream_t st, const float* scores = nullptr, int sld = 0) {
+                         SegWs& w, cudaStream_t st, const void* scores = nullptr, int sld = 0,
+                         int sdtype = VDET_DTYPE_F32) {
     if (scores != nullptr) {
-        k_score_keys<<<blocks_for(n), 256, 0, st>>>(scores, sld, n, w.keys, (uint32_t*)row_ids_out);
-        VDET_LAUNCH_CHECK();
-        int f0 = radix_sort_pairs(w.keys, (uint32_t*)row_ids_out, w.keys_alt, w.vals_alt, n, 0, 32, w.radix, st);
-        if (f0 != 0) { if (f0 > 0) set_error("segment: unexpected sort parity"); return f0 < 0 ? f0 : VDET_ERR_INVALID; }
+        const int rc0 = order_by_score(scores, sld, sdtype, n, w.keys, (uint32_t*)row_ids_out, w.keys_alt, w.vals_alt,
+                                       w.radix, st);
+        if (rc0 != VDET_OK) return rc0;
         k_frame_keys_perm<<<blocks_for(n), 256, 0, st>>>(frames, ld, n, row_valid, (const uint32_t*)row_ids_out,
                                                          w.keys, w.cnt);
     } else {
@@ -261,11 +309,12 @@ using namespace vdet;
 extern "C" size_t vdet_segment_workspace_bytes(int64_t n) { return seg_ws_bytes(n > 0 ? n : 1); }
 
 extern "C" int vdet_segment_by_frame(const float* frames, int ld, int64_t n, const uint8_t* row_valid,
-                                     const float* scores, int scores_ld,
+                                     const void* scores, int scores_ld, int scores_dtype,
                                      int32_t* row_ids_out, int32_t* seg_offsets_out, float* seg_frame_out,
                                      int32_t* n_segs_host, int32_t* max_seg_len_host, int64_t* n_packed_host,
                                      void* ws, size_t ws_bytes, void* stream) {
     VDET_REQUIRE(n >= 0 && n < 0x7fffffff && ld >= 1, "segment_by_frame: bad size");
+    VDET_REQUIRE(scores_dtype == VDET_DTYPE_F32 || scores_dtype == VDET_DTYPE_F64, "segment_by_frame: bad dtype");
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) {
         *n_segs_host = 0; *max_seg_len_host = 0; *n_packed_host = 0;
@@ -276,7 +325,8 @@ extern "C" int vdet_segment_by_frame(const float* frames, int ld, int64_t n, con
     WsCarver c(ws, ws_bytes);
     SegWs w;
     if (!carve_seg(c, n, w)) { set_error("segment_by_frame: workspace too small"); return VDET_ERR_WORKSPACE; }
-    int rc = segment_async(frames, ld, n, row_valid, row_ids_out, seg_offsets_out, seg_frame_out, w, st, scores, scores_ld);
+    int rc = segment_async(frames, ld, n, row_valid, row_ids_out, seg_offsets_out, seg_frame_out, w, st, scores, scores_ld,
+                           scores_dtype);
     if (rc != VDET_OK) return rc;
     SegCounters h;
     VDET_CUDA(cudaMemcpyAsync(&h, w.cnt, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -453,18 +503,17 @@ extern "C" int64_t vdet_track_det_nms_f32(const float* tracks, int64_t q, int tr
 }
 
 
-// ---- stable descending sort of (score, id) pairs (cross-rank keep-list merge) ----------------
-namespace vdet {
-__global__ void k_sort_keys(const float* __restrict__ scores, int64_t n, uint32_t* __restrict__ keys,
-                            uint32_t* __restrict__ vals) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    keys[p] = f32_key_desc(scores[p]);
-    vals[p] = (uint32_t)p;
+// ---- stable descending sort of (score, id) pairs (cross-rank keep-list merge, top_detections) -----
+extern "C" size_t vdet_sort_workspace_bytes(int64_t n) {
+    if (n < 1) n = 1;
+    return 4 * (size_t)(n + 1) * 4 + radix_scratch_elems(n) * 4 + 8 * 256;
 }
-__global__ void k_sort_gather(const uint32_t* __restrict__ perm, const float* __restrict__ scores,
-                              const int64_t* __restrict__ ids, int64_t n, float* __restrict__ scores_out,
-                              int64_t* __restrict__ ids_out) {
+
+namespace vdet {
+template <typename T>
+__global__ void k_sort_gather_t(const uint32_t* __restrict__ perm, const T* __restrict__ scores,
+                                const int64_t* __restrict__ ids, int64_t n, T* __restrict__ scores_out,
+                                int64_t* __restrict__ ids_out) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const uint32_t q = perm[p];
@@ -473,15 +522,11 @@ __global__ void k_sort_gather(const uint32_t* __restrict__ perm, const float* __
 }
 }  // namespace vdet
 
-extern "C" size_t vdet_sort_workspace_bytes(int64_t n) {
-    if (n < 1) n = 1;
-    return 4 * (size_t)(n + 1) * 4 + radix_scratch_elems(n) * 4 + 8 * 256;
-}
-
-extern "C" int vdet_sort_by_score_desc_f32(const float* scores, const int64_t* ids, int64_t n,
-                                           float* scores_out, int64_t* ids_out,
-                                           void* ws, size_t ws_bytes, void* stream) {
+extern "C" int vdet_sort_by_score_desc(const void* scores, int dtype, const int64_t* ids, int64_t n,
+                                       void* scores_out, int64_t* ids_out,
+                                       void* ws, size_t ws_bytes, void* stream) {
     VDET_REQUIRE(n >= 0 && n < 0x7fffffff, "sort_by_score: bad size");
+    VDET_REQUIRE(dtype == VDET_DTYPE_F32 || dtype == VDET_DTYPE_F64, "sort_by_score: bad dtype");
     if (n == 0) return VDET_OK;
     VDET_REQUIRE(scores != scores_out && ids != ids_out, "sort_by_score: in-place sort is not supported");
     cudaStream_t st = (cudaStream_t)stream;
@@ -492,11 +537,12 @@ extern "C" int vdet_sort_by_score_desc_f32(const float* scores, const int64_t* i
     uint32_t* va = c.take<uint32_t>(n + 1);
     uint32_t* radix = c.take<uint32_t>(radix_scratch_elems(n));
     if (!c.ok()) { set_error("sort_by_score: workspace too small"); return VDET_ERR_WORKSPACE; }
-    k_sort_keys<<<blocks_for(n), 256, 0, st>>>(scores, n, k, v);
-    VDET_LAUNCH_CHECK();
-    const int flip = radix_sort_pairs(k, v, ka, va, n, 0, 32, radix, st);
-    if (flip < 0) return flip;
-    k_sort_gather<<<blocks_for(n), 256, 0, st>>>(flip ? va : v, scores, ids, n, scores_out, ids_out);
+    const int rc = order_by_score(scores, 1, dtype, n, k, v, ka, va, radix, st);
+    if (rc != VDET_OK) return rc;
+    if (dtype == VDET_DTYPE_F32)
+        k_sort_gather_t<float><<<blocks_for(n), 256, 0, st>>>(v, (const float*)scores, ids, n, (float*)scores_out, ids_out);
+    else
+        k_sort_gather_t<double><<<blocks_for(n), 256, 0, st>>>(v, (const double*)scores, ids, n, (double*)scores_out, ids_out);
     VDET_LAUNCH_CHECK();
     return VDET_OK;
 }

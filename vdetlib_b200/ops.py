@@ -182,11 +182,14 @@ def segment_by_frame(frames, row_valid=None, scores=None):
     n_segs, max_len, n_packed = ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int64(0)
     if row_valid is not None:
         _need(row_valid, "row_valid", torch.uint8, 1)
-    sld = 0
+    sld, sdt = 0, _lib.DTYPE_F32
     if scores is not None:
-        _need(scores, "scores", torch.float32, 1)
+        _need(scores, "scores", None, 1)
+        if scores.dtype not in (torch.float32, torch.float64):
+            raise TypeError("segment_by_frame: float32 or float64 scores")
+        sdt = _lib.DTYPE_F32 if scores.dtype == torch.float32 else _lib.DTYPE_F64
         sld = scores.stride(0) if n > 1 else 1
-    rc = lib.vdet_segment_by_frame(_ptr(frames), ld, n, _ptr(row_valid), _ptr(scores), sld, _ptr(row_ids), _ptr(seg_off),
+    rc = lib.vdet_segment_by_frame(_ptr(frames), ld, n, _ptr(row_valid), _ptr(scores), sld, sdt, _ptr(row_ids), _ptr(seg_off),
                                    _ptr(seg_frame), ctypes.byref(n_segs), ctypes.byref(max_len),
                                    ctypes.byref(n_packed), _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, "segment_by_frame")
@@ -389,16 +392,19 @@ def tubelet_interpolate(knot_x, knot_y, knot_off, dense_first, dense_off):
 
 
 def sort_by_score_desc(scores, ids):
-    """Stable sort of (score f32, id i64) pairs by descending score (ties keep input order)."""
+    """Stable sort of (score f32|f64, id i64) pairs by descending score (ties keep input order)."""
     lib = _lib.load()
-    _need(scores, "scores", torch.float32, 1)
+    _need(scores, "scores", None, 1)
+    if scores.dtype not in (torch.float32, torch.float64):
+        raise TypeError("sort_by_score_desc: float32 or float64 scores")
+    dt = _lib.DTYPE_F32 if scores.dtype == torch.float32 else _lib.DTYPE_F64
     _need(ids, "ids", torch.int64, 1)
     scores, ids = scores.contiguous(), ids.contiguous()
     n = scores.numel()
     so, io = torch.empty_like(scores), torch.empty_like(ids)
     ws = _workspace(lib.vdet_sort_workspace_bytes(n) + 1024, scores.device)
-    _lib.check(lib.vdet_sort_by_score_desc_f32(_ptr(scores), _ptr(ids), n, _ptr(so), _ptr(io), _ptr(ws), ws.numel(),
-                                               _stream()), "sort_by_score_desc")
+    _lib.check(lib.vdet_sort_by_score_desc(_ptr(scores), dt, _ptr(ids), n, _ptr(so), _ptr(io), _ptr(ws), ws.numel(),
+                                           _stream()), "sort_by_score_desc")
     return so, io
 
 

@@ -58,26 +58,22 @@ def _class_scores(det_proto, class_index):
 def top_detections(det_proto, top_num, class_index):
     """The ``top_num`` highest-scoring detections of the video.  utils/protocol.py:330-339
     (stable descending sort; fewer than top_num detections -> a shallow copy, unsorted, :331-332).
-    The ranking is a stable radix sort on the GPU."""
+    The ranking is a stable radix sort of the float64 scores on the GPU."""
     import torch
     from .. import ops
     if len(det_proto['detections']) < top_num:
         return copy.copy(det_proto)
-    scores = _class_scores(det_proto, class_index)
-    s32 = scores.astype(np.float32)
-    if not np.array_equal(s32.astype(np.float64), scores):
-        # scores that are not float32-representable would change ties: rank on the host like the reference
-        order = sorted(range(len(scores)), key=lambda i: scores[i], reverse=True)
-    else:
-        ids = torch.arange(len(scores), dtype=torch.int64, device="cuda")
-        order = ops.sort_by_score_desc(torch.from_numpy(s32).cuda(), ids)[1].cpu().tolist()
+    scores = _class_scores(det_proto, class_index)                     # Python floats -> float64 keys
+    ids = torch.arange(len(scores), dtype=torch.int64, device="cuda")
+    order = ops.sort_by_score_desc(torch.from_numpy(scores).cuda(), ids)[1].cpu().tolist()
     dets = det_proto['detections']
     return {'video': det_proto['video'], 'detections': [dets[i] for i in order[:top_num]]}
 
 
 def frame_top_detections(det_proto, top_num, class_index):
     """The ``top_num`` best detections of every frame.  utils/protocol.py:341-351 (frames visited in
-    the iteration order of ``set(frames)`` like the reference, stable descending sort inside a frame)."""
+    the iteration order of ``set(frames)`` like the reference, stable descending sort inside a frame:
+    one stable sort by score then by frame on the GPU)."""
     import torch
     from .. import ops
     new_det = {'video': det_proto['video'], 'detections': []}
@@ -86,23 +82,16 @@ def frame_top_detections(det_proto, top_num, class_index):
         return new_det
     frame_idx = list(set([d['frame'] for d in dets]))
     scores = _class_scores(det_proto, class_index)
-    s32 = scores.astype(np.float32)
     frames = np.asarray([d['frame'] for d in dets], dtype=np.float32)
-    exact = np.array_equal(s32.astype(np.float64), scores) and np.array_equal(frames, [d['frame'] for d in dets])
-    if exact:
-        row_ids, seg_off, seg_frame, _ = ops.segment_by_frame(torch.from_numpy(frames).cuda(), None,
-                                                               torch.from_numpy(s32).cuda())
-        row_ids, seg_off = row_ids.cpu().numpy(), seg_off.cpu().numpy()
-        seg_of = {float(f): s for s, f in enumerate(seg_frame.cpu().tolist())}
+    if not np.array_equal(frames.astype(np.float64), np.asarray([d['frame'] for d in dets], dtype=np.float64)):
+        raise NotImplementedError("frame ids must be exactly representable in float32 (|frame| < 2^24)")
+    row_ids, seg_off, seg_frame, _ = ops.segment_by_frame(torch.from_numpy(frames).cuda(), None,
+                                                           torch.from_numpy(scores).cuda())
+    row_ids, seg_off = row_ids.cpu().numpy(), seg_off.cpu().numpy()
+    seg_of = {float(f): s for s, f in enumerate(seg_frame.cpu().tolist())}
     for frame_id in frame_idx:
-        if exact:
-            s = seg_of[float(np.float32(frame_id))]
-            ranked = row_ids[seg_off[s]:seg_off[s + 1]][:top_num]
-            new_det['detections'].extend(dets[i] for i in ranked)
-        else:
-            cur = sorted([d for d in dets if d['frame'] == frame_id],
-                         key=lambda x: det_score(x, class_index), reverse=True)
-            new_det['detections'].extend(cur[:top_num])
+        s = seg_of[float(np.float32(frame_id))]
+        new_det['detections'].extend(dets[i] for i in row_ids[seg_off[s]:seg_off[s + 1]][:top_num])
     return new_det
 
 
