@@ -44,8 +44,6 @@ def test_protocol_helpers():
     assert tub[0]["boxes"][0] == {"frame": 1, "bbox": [0, 0, 1, 1], "anchor": 0, "track_score": 0.25, "det_score": -1e5}
     assert "score" in tracks[0][0]                       # the input track is untouched (shallow copy per box)
     assert tub[0]["class"] == imagenet_vdet_classes[5] and tub[0]["gt"] == 0
-    dp = {"video": "v", "detections": [{"frame": 1 + i % 2, "scores": [{"class_index": 1, "score": i / 10.0}]} for i in range(6)]}
-    top = protocol.top_detections(dp, 2, 1)
-    assert [protocol.det_score(d, 1) for d in top["detections"]] == [0.5, 0.4]
-    ftop = protocol.frame_top_detections(dp, 1, 1)
-    assert sorted(protocol.det_score(d, 1) for d in ftop["detections"]) == [0.4, 0.5]
+    # top_detections / frame_top_detections rank on the GPU: covered by tests/test_gpu_temporal_tubelet.py
+    dp = {"video": "v", "detections": [{"frame": 1, "scores": [{"class_index": 1, "score": 0.1}]}]}
+    assert protocol.top_detections(dp, 5, 1) == dp                 # fewer than top_num: shallow copy (:331-332)
