@@ -245,3 +245,25 @@ def test_overlap_merge_top_golden():
     assert [d['hash'] for d in protocol.top_detections(copy.deepcopy(det), 50, 2)['detections']] == out["top_50"]
     assert [d['hash'] for d in protocol.top_detections(copy.deepcopy(det), 100000, 2)['detections']] == out["top_all"]
     assert [d['hash'] for d in protocol.frame_top_detections(copy.deepcopy(det), 5, 4)['detections']] == out["frame_top_5"]
+
+
+def test_big_frames_track_step_and_topk():
+    """Frames with more than 1024 detections (config 5 has 2000 per frame)."""
+    T, N, C = 3, 2000, 3
+    boxes, scores = synth.boxes_scores(T, N, C, seed=61, integer=True, frame_offset=1e-5)
+    vid = synth.vid_proto(T)
+    det_info = np.concatenate([np.repeat(np.arange(1, T + 1), N)[:, None].astype(np.float64),
+                               boxes.reshape(-1, 4).astype(np.float64), scores.reshape(-1, C).astype(np.float64)], axis=1)
+    opts = helpers.Opts(max_tracks=6, thres=0.2, nms_thres=0.3)
+    want, _ = oracle_np.greedily_track_from_raw_dets(vid, det_info, helpers.fake_tracker, 2, opts)
+    assert track.greedily_track_from_raw_dets(vid, det_info, helpers.fake_tracker, 2, opts) == want
+    rng = np.random.default_rng(14)
+    R, Ck = 2500, 4
+    sc = rng.permuted(np.tile(np.linspace(0.0, 0.4, R), (2, Ck, 1)), axis=-1).transpose(0, 2, 1).astype(np.float32)
+    sc[:, :, 2] *= 0.13
+    bx = rng.uniform(0, 500, (2, R, 4 * Ck)).astype(np.float32)
+    got = video_det.threshold_topk_frames(sc, bx, thresh=0.05, max_per_image=100)
+    for t in range(2):
+        want = oracle_np.threshold_topk_frame(sc[t], bx[t], 0.05, 100)
+        for j in range(1, Ck):
+            assert np.array_equal(got[j][t], want[j]), (t, j)
