@@ -256,6 +256,11 @@ def test_frame_major_layout_and_pipelined_postprocessor():
         assert np.array_equal(got, ls) and np.array_equal(out["link_iou"][:(T2 - 1) * N2].reshape(T2 - 1, N2), lb)
         dev_out = pp.run_device(pp.d_boxes, pp.d_scores)
         assert np.array_equal(dev_out["keep_idx"].cpu().numpy(), np.where(ki2 >= 0, ki2 + (np.arange(T2) * N2)[:, None, None], -1))
+        for _ in range(3):                                           # CUDA-graph replay of the same step
+            pp.d_mask.zero_(); pp.d_succ.zero_()
+            g_out = pp.run_device(pp.d_boxes, pp.d_scores, graph=True)
+            assert np.array_equal(g_out["keep_mask"].cpu().numpy(), km2)
+            assert np.array_equal(g_out["succ"].cpu().numpy(), out["succ"])
 
 
 def test_sort_by_score_desc():

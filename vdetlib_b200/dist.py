@@ -85,12 +85,15 @@ class ShardedVideoPostProcessor(object):
 
     def step_device(self, d_boxes, d_scores):
         """Device-resident inputs; returns the result dict of VideoPostProcessor.run_device.
+        On a single rank there is no exchange and the step is replayed from a CUDA graph.
 
         The boundary all-gather is enqueued first, on a side stream, and overlaps the NMS kernel: with
         more than one rank a few SMs are kept out of the persistent NMS grid (vdet_set_reserved_sms)
         so that the NCCL kernel is scheduled immediately; the link kernel then waits on it."""
         from . import ops
         pp = self.pp
+        if self.exchange.world == 1:
+            return pp.run_device(d_boxes, d_scores, None, graph=True)
         main = torch.cuda.current_stream()
         halo = self._exchange(d_boxes[:self.n_boxes])
         out = ops.nms_frames(d_boxes, d_scores, pp.seg_offsets, pp.nms_thresh, pp.N, want_mask=True,

@@ -107,6 +107,7 @@ class VideoPostProcessor(object):
         self.chunk_seg = {f1 - f0: ops.seg_offsets_uniform(f1 - f0, N, dev) for f0, f1 in self.chunks}
         self.s_in = torch.cuda.Stream(device=dev)
         self.s_out = torch.cuda.Stream(device=dev)
+        self._graphs = {}
 
     # bytes crossing PCIe per run_staged() call
     @property
@@ -121,13 +122,34 @@ class VideoPostProcessor(object):
         T, N, C = self.T, self.N, self.C
         return {"keep_idx": out[0].view(T, C, N), "keep_cnt": out[1], "keep_mask": out[2].view(T, C, N)}
 
-    def run_device(self, d_boxes, d_scores, halo=None):
-        """Device tensors in ([T*N,4], [T*N,C]), device tensors out; asynchronous, one launch each."""
+    def _launch(self, d_boxes, d_scores, halo):
         out = ops.nms_frames(d_boxes, d_scores, self.seg_offsets, self.nms_thresh, self.N, want_mask=True,
                              status=self.status, frame_major_out=True, out=(self.d_idx, self.d_cnt, self.d_mask))
-        succ, link_iou = ops.link_frames(d_boxes, self.seg_offsets, self.N, halo)
+        ops.link_frames(d_boxes, self.seg_offsets, self.N, halo, out=(self.d_succ, self.d_iou))
+        return out
+
+    def run_device(self, d_boxes, d_scores, halo=None, graph=False):
+        """Device tensors in ([T*N,4], [T*N,C]), device tensors out; asynchronous.
+
+        ``graph=True`` replays the two launches (NMS, link) from a CUDA graph captured on first use for
+        this pair of input buffers -- no per-step launch overhead or inter-kernel gap.  Outputs always
+        live in the processor's own buffers (valid until the next call)."""
+        if not graph:
+            out = self._launch(d_boxes, d_scores, halo)
+        else:
+            key = (d_boxes.data_ptr(), d_scores.data_ptr(), 0 if halo is None else halo.data_ptr())
+            g = self._graphs.get(key)
+            if g is None:
+                self._launch(d_boxes, d_scores, halo)                    # warm up outside the capture
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch(d_boxes, d_scores, halo)
+                self._graphs[key] = g
+            g.replay()
+            out = (self.d_idx, self.d_cnt, self.d_mask)
         res = self._views(out)
-        res.update(succ=succ, link_iou=link_iou)
+        res.update(succ=self.d_succ, link_iou=self.d_iou)
         return res
 
     def stage(self, boxes, scores):
