@@ -125,28 +125,30 @@ template <> struct Vec16<double> { typedef double2 type; static constexpr int V 
 //   trailing run -> l                       (:296-298)
 //   interior     -> l + (r - l) * (k - i + 1) / (j - i + 1)     (:299-303)
 // Streaming formulation (one read + one write of the row, any row length): rows are cut into
-// 1024-element tiles.
-//   pass 1 (completion_bounds_kernel, one warp per tile): the nearest valid element to the LEFT of
-//          the tile and to the RIGHT of it (index + value) -- a ballot search that normally ends
-//          in its first 32-element probe -- goes to a small side buffer.  Reading neighbours in a
-//          separate pass keeps the in-place update of pass 2 race-free.
-//   pass 2 (completion_fill_kernel, one CTA per tile): 16-byte loads, block-wide max-scan of "last
-//          valid index" and min-scan of "next valid index" (warp shuffles + one shared-memory
-//          hop), closed form per missing element, 16-byte stores.
-constexpr int CP_THREADS = 256;
-constexpr int CP_ITEMS = 8;
-constexpr int CP_TILE = CP_THREADS * CP_ITEMS;
+// 256-element tiles, one warp each.
+//   pass 1 (completion_bounds_kernel): for tiles whose first / last element is missing, the nearest
+//          valid element to the LEFT / RIGHT of the tile (index + value) -- a ballot search that
+//          normally ends in its first 32-element probe -- goes to a small side buffer.  Reading
+//          neighbours in a separate pass keeps the in-place update of pass 2 race-free.
+//   pass 2 (completion_fill_kernel): 16-byte loads, warp max-scan of "last valid index" and min-scan
+//          of "next valid index" (shuffles only, no block barrier), closed form per missing
+//          element, 16-byte stores by the lanes that changed something; tiles without a missing
+//          element return after the load.
+constexpr int CP_ITEMS = 8;                    // elements per lane
+constexpr int CP_TILE = 32 * CP_ITEMS;         // one warp = one 256-element tile
+constexpr int CP_WARPS = 8;                    // tiles per CTA (independent of each other)
 
 template <typename T>
 struct TileBounds { int32_t left_idx; int32_t right_idx; T left_val; T right_val; };
 
+// Pass 1: only tiles whose first / last element is missing need a neighbour outside the tile.
+// One THREAD per tile (two loads); the rare tiles that do need a neighbour walk outwards serially.
 template <typename T>
 __global__ void __launch_bounds__(256) completion_bounds_kernel(const T* __restrict__ scores, int64_t L, int64_t ld,
                                                                 const int32_t* __restrict__ lengths,
                                                                 int tiles_per_row, int64_t n_tiles, T miss_thr,
                                                                 TileBounds<T>* __restrict__ bounds) {
-    const int lane = threadIdx.x & 31;
-    const int64_t tile_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t tile_id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tile_id >= n_tiles) return;
     const int64_t row = tile_id / tiles_per_row;
     const int tile = (int)(tile_id - row * tiles_per_row);
@@ -155,135 +157,138 @@ __global__ void __launch_bounds__(256) completion_bounds_kernel(const T* __restr
     if (t0 >= len) return;
     const int t1 = (t0 + CP_TILE < len) ? t0 + CP_TILE : len;
     const T* g = scores + row * ld;
+    const bool need_left = g[t0] <= miss_thr, need_right = g[t1 - 1] <= miss_thr;
+    if (!need_left && !need_right) return;
     TileBounds<T> b;
     b.left_idx = -1; b.right_idx = len; b.left_val = (T)0; b.right_val = (T)0;
-    for (int base = t0 - 1; base >= 0; base -= 32) {            // nearest valid element left of the tile
-        const int k = base - lane;
-        const T v = k >= 0 ? g[k] : (T)0;
-        const unsigned hit = __ballot_sync(FULL, k >= 0 && !(v <= miss_thr));
-        if (hit) {
-            const int l = __ffs(hit) - 1;
-            b.left_idx = base - l;
-            b.left_val = __shfl_sync(FULL, v, l);
-            break;
+    if (need_left) {
+        for (int k = t0 - 1; k >= 0; --k) {                     // nearest valid element left of the tile
+            const T v = g[k];
+            if (!(v <= miss_thr)) { b.left_idx = k; b.left_val = v; break; }
         }
     }
-    for (int base = t1; base < len; base += 32) {               // nearest valid element right of it
-        const int k = base + lane;
-        const T v = k < len ? g[k] : (T)0;
-        const unsigned hit = __ballot_sync(FULL, k < len && !(v <= miss_thr));
-        if (hit) {
-            const int l = __ffs(hit) - 1;
-            b.right_idx = base + l;
-            b.right_val = __shfl_sync(FULL, v, l);
-            break;
+    if (need_right) {
+        for (int k = t1; k < len; ++k) {                        // nearest valid element right of it
+            const T v = g[k];
+            if (!(v <= miss_thr)) { b.right_idx = k; b.right_val = v; break; }
         }
     }
-    if (lane == 0) bounds[tile_id] = b;
+    bounds[tile_id] = b;
 }
 
+// Pass 2: persistent warps, one 256-element tile at a time, no block barrier.  Lanes load 8
+// consecutive elements (16-byte loads) and publish them plus an 8-bit validity mask in the warp's
+// shared scratch.  The tile's MISSING elements are then dealt out evenly over the lanes (ballots per
+// position + __fns pick the m-th one): missing elements are ~5 % of a row, so one pass of the closed
+// form serves the whole tile -- walking each lane's own 8 positions instead would make every warp
+// execute the divergent body 8 times (first version: 489 instructions per tile).  Last / next valid
+// index come from the 256-bit validity set, values from the scratch or the tile's boundary record.
 template <typename T>
-__global__ void __launch_bounds__(CP_THREADS) completion_fill_kernel(T* __restrict__ scores, int64_t L, int64_t ld,
-                                                                     const int32_t* __restrict__ lengths,
-                                                                     int tiles_per_row, T miss_thr, int vec_ok,
-                                                                     const TileBounds<T>* __restrict__ bounds,
-                                                                     uint32_t* status) {
-    __shared__ T s_val[CP_TILE];
-    __shared__ int32_t s_wl[CP_THREADS / 32], s_wr[CP_THREADS / 32];
-    const int64_t tile_id = blockIdx.x;
-    const int64_t row = tile_id / tiles_per_row;
-    const int tile = (int)(tile_id - row * tiles_per_row);
-    const int len = (int)(lengths ? (int64_t)lengths[row] : L);
-    const int t0 = tile * CP_TILE;
-    if (t0 >= len) return;
-    T* g = scores + row * ld;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int e0 = t0 + tid * CP_ITEMS;                       // this thread's 4 consecutive elements
-    T v[CP_ITEMS];
+__global__ void __launch_bounds__(CP_WARPS * 32) completion_fill_kernel(T* __restrict__ scores, int64_t L, int64_t ld,
+                                                                        const int32_t* __restrict__ lengths,
+                                                                        int tiles_per_row, int64_t n_tiles, T miss_thr,
+                                                                        int vec_ok,
+                                                                        const TileBounds<T>* __restrict__ bounds,
+                                                                        uint32_t* status) {
+    __shared__ __align__(16) T s_val_all[CP_WARPS][CP_TILE];
+    __shared__ __align__(16) uint32_t s_ok_all[CP_WARPS][8];      // 256 validity bits per tile
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T* s_val = s_val_all[warp];
+    uint32_t* s_ok = s_ok_all[warp];
     constexpr int V = 16 / sizeof(T);
-    if (vec_ok && e0 + CP_ITEMS <= len) {
-#pragma unroll
-        for (int q = 0; q < CP_ITEMS; q += V) {
-            const typename Vec16<T>::type x = *reinterpret_cast<const typename Vec16<T>::type*>(g + e0 + q);
-            const T* px = reinterpret_cast<const T*>(&x);
-#pragma unroll
-            for (int c = 0; c < V; ++c) v[q + c] = px[c];
-        }
-    } else {
-#pragma unroll
-        for (int q = 0; q < CP_ITEMS; ++q) v[q] = (e0 + q < len) ? g[e0 + q] : (T)0;
-    }
-    bool ok[CP_ITEMS];
-    int my_last = -1, my_first = 0x7fffffff;
-#pragma unroll
-    for (int q = 0; q < CP_ITEMS; ++q) {
-        ok[q] = (e0 + q < len) && !(v[q] <= miss_thr);
-        s_val[tid * CP_ITEMS + q] = v[q];
-        if (ok[q]) { my_last = e0 + q; if (my_first == 0x7fffffff) my_first = e0 + q; }
-    }
-    // exclusive max-scan (threads before me) of my_last, exclusive min-scan (threads after me) of my_first
-    int incl_l = my_last, incl_r = my_first;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int a = __shfl_up_sync(FULL, incl_l, d);
-        const int c = __shfl_down_sync(FULL, incl_r, d);
-        if (lane >= d) incl_l = max(incl_l, a);
-        if (lane + d < 32) incl_r = min(incl_r, c);
-    }
-    if (lane == 31) s_wl[warp] = incl_l;
-    if (lane == 0) s_wr[warp] = incl_r;
-    __syncthreads();
-    int before = __shfl_up_sync(FULL, incl_l, 1);
-    if (lane == 0) before = -1;
-    int after = __shfl_down_sync(FULL, incl_r, 1);
-    if (lane == 31) after = 0x7fffffff;
-    for (int w = 0; w < warp; ++w) before = max(before, s_wl[w]);
-    for (int w = warp + 1; w < CP_THREADS / 32; ++w) after = min(after, s_wr[w]);
-    const TileBounds<T> b = bounds[tile_id];
-    const int t1 = (t0 + CP_TILE < len) ? t0 + CP_TILE : len;
-    bool changed = false;
-    // last valid index at or before each element / next valid index at or after it
-    int lastv[CP_ITEMS], nextv[CP_ITEMS];
-    int run = before;
-#pragma unroll
-    for (int q = 0; q < CP_ITEMS; ++q) { if (ok[q]) run = e0 + q; lastv[q] = run; }
-    run = after;
-#pragma unroll
-    for (int q = CP_ITEMS - 1; q >= 0; --q) { if (ok[q]) run = e0 + q; nextv[q] = run; }
-#pragma unroll
-    for (int q = 0; q < CP_ITEMS; ++q) {
-        const int k = e0 + q;
-        if (k >= len || ok[q] || !(v[q] <= miss_thr)) continue;          // valid or NaN: untouched
-        int i, j;                 // run = [i, j)
-        T lft, rgt;
-        if (lastv[q] >= t0) { i = lastv[q] + 1; lft = s_val[lastv[q] - t0]; }
-        else { i = b.left_idx + 1; lft = b.left_val; }
-        if (nextv[q] < t1) { j = nextv[q]; rgt = s_val[nextv[q] - t0]; }
-        else { j = b.right_idx; rgt = b.right_val; }
-        T r;
-        if (i == 0) {
-            if (j >= len) { if (k == 0) atomicOr(status, VDET_STATUS_ALL_MISSING); continue; }
-            r = rgt;
-        } else if (j >= len) {
-            r = lft;
-        } else {
-            r = t_add(lft, t_div(t_mul(t_sub(rgt, lft), (T)(k - i + 1)), (T)(j - i + 1)));
-        }
-        v[q] = r;
-        changed = true;
-    }
-    // s_val is read above by other threads: writes go to global only
-    if (vec_ok && e0 + CP_ITEMS <= len) {
-        if (changed) {                                                    // untouched threads skip the store
+    for (int64_t tile_id = (int64_t)blockIdx.x * CP_WARPS + warp; tile_id < n_tiles;
+         tile_id += (int64_t)gridDim.x * CP_WARPS) {
+        const int64_t row = tile_id / tiles_per_row;
+        const int tile = (int)(tile_id - row * tiles_per_row);
+        const int len = (int)(lengths ? (int64_t)lengths[row] : L);
+        const int t0 = tile * CP_TILE;
+        if (t0 >= len) continue;
+        T* g = scores + row * ld;
+        const int e0 = t0 + lane * CP_ITEMS;                   // this lane's 8 consecutive elements
+        __align__(16) T v[CP_ITEMS];
+        if (vec_ok && e0 + CP_ITEMS <= len) {
 #pragma unroll
             for (int q = 0; q < CP_ITEMS; q += V)
-                *reinterpret_cast<typename Vec16<T>::type*>(g + e0 + q) =
-                    *reinterpret_cast<const typename Vec16<T>::type*>(v + q);
-        }
-    } else if (changed) {
+                *reinterpret_cast<typename Vec16<T>::type*>(v + q) =
+                    *reinterpret_cast<const typename Vec16<T>::type*>(g + e0 + q);
+        } else {
 #pragma unroll
-        for (int q = 0; q < CP_ITEMS; ++q)
-            if (e0 + q < len) g[e0 + q] = v[q];
+            for (int q = 0; q < CP_ITEMS; ++q) v[q] = (e0 + q < len) ? g[e0 + q] : (T)0;
+        }
+        unsigned okm = 0, missm = 0;                           // bit q: element q valid / missing
+#pragma unroll
+        for (int q = 0; q < CP_ITEMS; ++q) {
+            const bool in = e0 + q < len;
+            const bool miss = v[q] <= miss_thr;
+            if (in && !miss) okm |= 1u << q;
+            if (in && miss) missm |= 1u << q;
+        }
+        if (!__any_sync(FULL, missm != 0)) continue;           // nothing to fill in this tile
+        __syncwarp();                                          // previous tile's readers are done
+#pragma unroll
+        for (int q = 0; q < CP_ITEMS; q += V)
+            *reinterpret_cast<typename Vec16<T>::type*>(s_val + lane * CP_ITEMS + q) =
+                *reinterpret_cast<const typename Vec16<T>::type*>(v + q);
+        reinterpret_cast<uint8_t*>(s_ok)[lane] = (uint8_t)okm;
+        // where are the missing elements?  cq[q] = lanes whose element q is missing
+        unsigned cq[CP_ITEMS];
+        int total = 0;
+#pragma unroll
+        for (int q = 0; q < CP_ITEMS; ++q) {
+            cq[q] = __ballot_sync(FULL, (missm >> q) & 1u);
+            total += __popc(cq[q]);
+        }
+        __syncwarp();
+        const uint4 w_lo = *reinterpret_cast<const uint4*>(s_ok), w_hi = *reinterpret_cast<const uint4*>(s_ok + 4);
+        const uint32_t okw[8] = {w_lo.x, w_lo.y, w_lo.z, w_lo.w, w_hi.x, w_hi.y, w_hi.z, w_hi.w};
+        for (int m = lane; m < total; m += 32) {
+            // the m-th missing element (position-major order): position q, then the lane owning it
+            int q = 0, rest = m;
+#pragma unroll
+            for (int qq = 0; qq < CP_ITEMS - 1; ++qq) {
+                const int c = __popc(cq[qq]);
+                if (q == qq && rest >= c) { rest -= c; q = qq + 1; }
+            }
+            unsigned sel = cq[0];
+#pragma unroll
+            for (int qq = 1; qq < CP_ITEMS; ++qq) sel = (q == qq) ? cq[qq] : sel;
+            const int src = __fns(sel, 0, rest + 1);           // lane that owns it
+            const int e = src * CP_ITEMS + q;                  // element index inside the tile
+            const int k = t0 + e;
+            // last valid element before e / first valid element after e, inside the tile
+            int lv = -1, nv = 0x7fffffff;
+#pragma unroll
+            for (int w = 7; w >= 0; --w) {
+                unsigned mword = okw[w];
+                if (w == (e >> 5)) mword &= (1u << (e & 31)) - 1u;
+                if (w <= (e >> 5) && lv < 0 && mword) lv = w * 32 + 31 - __clz(mword);
+            }
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                unsigned mword = okw[w];
+                if (w == (e >> 5)) mword &= ~((2u << (e & 31)) - 1u);
+                if (w >= (e >> 5) && nv == 0x7fffffff && mword) nv = w * 32 + __ffs(mword) - 1;
+            }
+            int i, j;             // run = [i, j) in row coordinates
+            T lft, rgt;
+            TileBounds<T> b;
+            b.left_idx = -1; b.right_idx = len; b.left_val = (T)0; b.right_val = (T)0;
+            if (lv < 0 || nv == 0x7fffffff) b = bounds[tile_id];   // a run that touches the tile edge
+            if (lv >= 0) { i = t0 + lv + 1; lft = s_val[lv]; }
+            else { i = b.left_idx + 1; lft = b.left_val; }
+            if (nv != 0x7fffffff) { j = t0 + nv; rgt = s_val[nv]; }
+            else { j = b.right_idx; rgt = b.right_val; }
+            T r;
+            if (i == 0) {
+                if (j >= len) { if (k == 0) atomicOr(status, VDET_STATUS_ALL_MISSING); continue; }
+                r = rgt;
+            } else if (j >= len) {
+                r = lft;
+            } else {
+                r = t_add(lft, t_div(t_mul(t_sub(rgt, lft), (T)(k - i + 1)), (T)(j - i + 1)));
+            }
+            g[k] = r;
+        }
     }
 }
 
@@ -454,12 +459,15 @@ static int run_completion(void* scores, int64_t n_rows, int64_t L, int64_t ld, c
         return VDET_ERR_WORKSPACE;
     }
     TileBounds<T>* bounds = (TileBounds<T>*)ws;
-    completion_bounds_kernel<T><<<(unsigned)((n_tiles + 7) / 8), 256, 0, st>>>((const T*)scores, L, ld, lengths,
+    completion_bounds_kernel<T><<<(unsigned)((n_tiles + 255) / 256), 256, 0, st>>>((const T*)scores, L, ld, lengths,
                                                                               (int)tiles, n_tiles, (T)miss_thr, bounds);
     VDET_LAUNCH_CHECK();
     const int vec_ok = (((uintptr_t)scores & 15) == 0 && (ld % (16 / sizeof(T))) == 0) ? 1 : 0;
-    completion_fill_kernel<T><<<(unsigned)n_tiles, CP_THREADS, 0, st>>>((T*)scores, L, ld, lengths, (int)tiles,
-                                                                         (T)miss_thr, vec_ok, bounds, status);
+    int64_t fill_grid = (n_tiles + CP_WARPS - 1) / CP_WARPS;
+    const int64_t fill_cap = (int64_t)sm_count_cached() * 8;          // 8 resident CTAs per SM
+    if (fill_grid > fill_cap) fill_grid = fill_cap;
+    completion_fill_kernel<T><<<(unsigned)fill_grid, CP_WARPS * 32, 0, st>>>(
+        (T*)scores, L, ld, lengths, (int)tiles, n_tiles, (T)miss_thr, vec_ok, bounds, status);
     VDET_LAUNCH_CHECK();
     return VDET_OK;
 }
