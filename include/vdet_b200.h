@@ -247,6 +247,20 @@ int vdet_tubelet_interpolate_f64(const double* knot_x, const double* knot_y, int
                                  void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Links -> tubelet score rows (build-defined glue between vdet_link_frames_f32 and the temporal
+ * kernels; the reference obtains tubelets from external trackers, vdet/track.py:18-106).
+ *   follow_links: chain k starts at packed row start[k] and follows succ[]; it ends at succ == -1
+ *                 or when link_iou < min_iou.  chain_rows [n_frames, n_chains] int32 (-1 after the end).
+ *   gather_chain_scores: out [n_chains, n_classes, n_frames] float32 = class scores along each chain,
+ *                 `missing` (-1e5, utils/protocol.py:459) after its end -- the rows that
+ *                 vdet_score_completion / vdet_temporal_maxpool / vdet_temporal_conv1d consume.
+ * ------------------------------------------------------------------------------------- */
+int vdet_follow_links(const int32_t* succ, const float* link_iou, const int32_t* start, int n_chains,
+                      int n_frames, float min_iou, int32_t* chain_rows, void* stream);
+int vdet_gather_chain_scores_f32(const float* scores, int n_classes, const int32_t* chain_rows,
+                                 int n_chains, int n_frames, float missing, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Stable sort of (score, id) pairs by DESCENDING score (equal scores keep their input order).
  * The merge step of a frame-sharded vid_nms: every rank all-gathers its kept (score, global row)
  * list and sorts the concatenation into the reference's global keep order (utils/nms.pyx:80,97);

@@ -164,3 +164,29 @@ def test_nms_generic_path_on_weird_boxes():
                 gpu.nms(d, thr)
         else:
             assert gpu.nms(d, thr) == want
+
+
+def test_follow_links_and_gather_rows():
+    """Links -> tubelet score rows (build-defined glue): against a direct NumPy walk."""
+    T, N, C = 12, 90, 4
+    b, s = synth.boxes_scores(T, N, C, seed=21)
+    dev = torch.device(DEV)
+    db = torch.from_numpy(b.reshape(-1, 4)).to(dev)
+    ds = torch.from_numpy(s.reshape(-1, C)).to(dev)
+    succ, best = ops.link_frames(db, ops.seg_offsets_uniform(T, N, dev), N)
+    start = torch.arange(0, N, dtype=torch.int32, device=dev)
+    for min_iou in (0.0, 0.2):
+        rows = ops.follow_links(succ, best, start, T, min_iou).cpu().numpy()
+        sn, bn = succ.cpu().numpy(), best.cpu().numpy()
+        want = np.full((T, N), -1, np.int32)
+        for k in range(N):
+            r = k
+            for t in range(T):
+                want[t, k] = r
+                if r >= 0:
+                    r = sn[r] if (sn[r] >= 0 and bn[r] >= np.float32(min_iou)) else -1
+        assert np.array_equal(rows, want)
+        out = ops.gather_chain_scores(ds, torch.from_numpy(rows).to(dev)).cpu().numpy()
+        sflat = s.reshape(-1, C)
+        ref = np.where(want.T[:, None, :] >= 0, sflat[np.maximum(want.T, 0)].transpose(0, 2, 1), np.float32(-1e5))
+        assert np.array_equal(out, ref)

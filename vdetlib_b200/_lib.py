@@ -48,6 +48,8 @@ SIGNATURES = {
     "vdet_temporal_maxpool": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _i32, _f64, _vp]),
     "vdet_temporal_conv1d": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _vp]),
     "vdet_tubelet_interpolate_f64": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp]),
+    "vdet_follow_links": (_i32, [_vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp]),
+    "vdet_gather_chain_scores_f32": (_i32, [_vp, _i32, _vp, _i32, _i32, _f32, _vp, _vp]),
     "vdet_sort_workspace_bytes": (_sz, [_i64]),
     "vdet_sort_by_score_desc": (_i32, [_vp, _i32, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "vdet_threshold_topk_f32": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _i32, _vp, _vp, _vp]),

@@ -391,6 +391,34 @@ def tubelet_interpolate(knot_x, knot_y, knot_off, dense_first, dense_off):
     return out
 
 
+def follow_links(succ, link_iou, start_rows, n_frames, min_iou=0.0):
+    """Follow the frame-to-frame links from ``start_rows`` for ``n_frames`` frames.
+    Returns chain_rows i32 [n_frames, K] (packed row per frame, -1 after a chain ended)."""
+    lib = _lib.load()
+    _need(succ, "succ", torch.int32, 1)
+    _need(link_iou, "link_iou", torch.float32, 1)
+    _need(start_rows, "start_rows", torch.int32, 1)
+    K = start_rows.numel()
+    out = torch.empty((int(n_frames), K), dtype=torch.int32, device=succ.device)
+    _lib.check(lib.vdet_follow_links(_ptr(succ), _ptr(link_iou), _ptr(start_rows), K, int(n_frames), float(min_iou),
+                                     _ptr(out), _stream()), "follow_links")
+    return out
+
+
+def gather_chain_scores(scores, chain_rows, missing=MISSING):
+    """Class scores along every chain: [K, C, n_frames] f32 rows for the temporal kernels."""
+    lib = _lib.load()
+    _need(scores, "scores", torch.float32, 2)
+    _need(chain_rows, "chain_rows", torch.int32, 2)
+    scores = scores.contiguous()
+    T, K = chain_rows.shape
+    C = scores.shape[1]
+    out = torch.empty((K, C, T), dtype=torch.float32, device=scores.device)
+    _lib.check(lib.vdet_gather_chain_scores_f32(_ptr(scores), C, _ptr(chain_rows), K, T, float(missing), _ptr(out),
+                                                _stream()), "gather_chain_scores")
+    return out
+
+
 def sort_by_score_desc(scores, ids):
     """Stable sort of (score f32|f64, id i64) pairs by descending score (ties keep input order)."""
     lib = _lib.load()
