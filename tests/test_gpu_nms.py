@@ -219,6 +219,33 @@ def test_nms_any_length_frames():
         gpu.nms(z, 0.3)
 
 
+@pytest.mark.parametrize("n", [1100, 1500, 2046])
+def test_zero_division_big_frames(n):
+    """ZeroDivisionError semantics (visited pairs only, nms.pyx:64) in the 1025..2048-box kernel."""
+    rng = np.random.default_rng(n)
+    d = helpers.unique_score_dets(rng, n, scale=900.0)
+    deg = np.asarray([[5, 5, 4, 4, 0.0], [7, 7, 6, 6, 0.0]], np.float32)
+    for s0, s1 in ((0.001, 0.0005), (2.0, 1.5), (2.0, 0.0005)):
+        deg[0, 4], deg[1, 4] = s0, s1
+        z = np.concatenate([d[:n // 2], deg[:1], d[n // 2:], deg[1:]])
+        try:
+            want = c_oracle.nms(z, 0.3)
+        except ZeroDivisionError:
+            want = ZeroDivisionError
+        if want is ZeroDivisionError:
+            with pytest.raises(ZeroDivisionError):
+                gpu.nms(z, 0.3)
+        else:
+            assert gpu.nms(z, 0.3) == want
+    # one degenerate box alone has a positive union with every sane box: no error
+    z = np.concatenate([d, deg[:1]])
+    assert gpu.nms(z, 0.3) == c_oracle.nms(z, 0.3)
+    # threshold 0: the top box suppresses everything, the zero-union pair is never visited
+    deg[0, 4], deg[1, 4] = 0.001, 0.0005
+    z = np.concatenate([d, deg])
+    assert gpu.nms(z, 0.0) == c_oracle.nms(z, 0.0) == [int(np.argmax(z[:, 4]))]
+
+
 def test_frame_major_layout_and_pipelined_postprocessor():
     """Frame-major outputs (ragged frames) and the chunk-pipelined host API equal the oracle."""
     from vdetlib_b200.vdet.video_det import VideoPostProcessor

@@ -400,7 +400,13 @@ static int launch_nms_frames(const NmsFramesParams& p, size_t smem, int grid, cu
 //   * the removed set takes two words per lane; mask rows are read from the CTA's global slot.
 // ==========================================================================================
 constexpr int BIG_MAX = 2048;
+constexpr int BIG_NPER = BIG_MAX / 32;   // keys per lane of the register sort
+constexpr int BIG_SK_LD = BIG_MAX + 64;  // per-warp key/order scratch, skewed by one word per 32
 constexpr int BIG_ST_LD = 9;     // padded row of the transposed staging tile (8 words + 1)
+
+// Skew of the per-warp key/order scratch: the sorted keys leave the register network in blocked
+// layout (position half*1024 + lane*32 + r), so an unskewed store would put all 32 lanes on one bank.
+__device__ __forceinline__ int skw(const int q) { return q + (q >> 5); }
 
 __device__ __noinline__ void zero_division_check_big(const uint32_t* ord, int n, const float4* sbox,
                                                      const float* sarea, uint32_t rem0, uint32_t rem1, uint32_t ci,
@@ -411,7 +417,7 @@ __device__ __noinline__ void zero_division_check_big(const uint32_t* ord, int n,
     for (int base = pos + 1; base < n; base += 32) {             // warp-uniform trip count
         const int k2 = base + lane;
         const bool act = k2 < n;
-        const uint32_t j = act ? ord[k2] : 0u;
+        const uint32_t j = act ? ord[skw(k2)] : 0u;
         const uint32_t w0 = __shfl_sync(FULL, rem0, (int)((j >> 5) & 31));
         const uint32_t w1 = __shfl_sync(FULL, rem1, (int)((j >> 5) & 31));
         const uint32_t wj = ((j >> 5) & 32) ? w1 : w0;
@@ -428,13 +434,13 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_frames_big_kernel(const NmsFr
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NB = p.nb;            // multiple of 256
     const int W = NB >> 5;          // <= 64
-    const int NPAD = p.npad;
+    constexpr int NPAD = BIG_MAX;
     float4* sbox = reinterpret_cast<float4*>(smem_raw);
     float* sarea = reinterpret_cast<float*>(sbox + NB);
     int32_t* srow = reinterpret_cast<int32_t*>(sarea + NB);
     uint32_t* sT = reinterpret_cast<uint32_t*>(srow + NB);                  // [256][BIG_ST_LD]
-    uint32_t* skeys = sT + 256 * BIG_ST_LD;                                 // [NMS_WARPS][NPAD] keys, then order
-    uint16_t* srank = reinterpret_cast<uint16_t*>(skeys + NMS_WARPS * NPAD);  // [NMS_WARPS][NPAD]
+    uint32_t* skeys = sT + 256 * BIG_ST_LD;                                 // [NMS_WARPS][BIG_SK_LD] keys, then order
+    uint16_t* srank = reinterpret_cast<uint16_t*>(skeys + NMS_WARPS * BIG_SK_LD);  // [NMS_WARPS][NPAD]
     uint16_t* scnt = srank + NMS_WARPS * NPAD;                              // [NMS_WARPS][NPAD] tie counters
     __shared__ int s_zero_union;
     uint32_t* gmask = p.gmask + (size_t)blockIdx.x * NB * W;
@@ -442,7 +448,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_frames_big_kernel(const NmsFr
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C = p.n_classes;
     const float T = p.thresh_f32;
-    uint32_t* sk = skeys + (size_t)warp * NPAD;
+    uint32_t* sk = skeys + (size_t)warp * BIG_SK_LD;
     uint16_t* rk = srank + (size_t)warp * NPAD;
     uint16_t* ct = scnt + (size_t)warp * NPAD;
 
@@ -540,25 +546,36 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_frames_big_kernel(const NmsFr
             auto score_key = [&](const int e) -> uint32_t {
                 return f32_key_desc(__ldg(sc_glob + (int64_t)srow[e] * p.score_ldr));
             };
-            // -- keys, sorted ascending in shared memory (= descending score)
-            for (int e = lane; e < NPAD; e += 32) sk[e] = e < n ? score_key(e) : 0xffffffffu;
-            __syncwarp();
-            for (int size = 2; size <= NPAD; size <<= 1) {
-                for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                    for (int t = lane; t < (NPAD >> 1); t += 32) {
-                        const int i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
-                        const int j = i + stride;
-                        const uint32_t a = sk[i], b = sk[j];
-                        const bool up = (i & size) == 0;
-                        sk[i] = up ? min(a, b) : max(a, b);
-                        sk[j] = up ? max(a, b) : min(a, b);
-                    }
-                    __syncwarp();
+            // -- keys: 64 per lane through the register network (ascending key = descending score),
+            //    then parked in shared memory for the rank search
+            bool tie = false;
+            {
+                constexpr int H = BIG_NPER / 2;                   // 32 keys per lane and half
+                uint32_t klo[H], khi[H];
+#pragma unroll
+                for (int r = 0; r < H; ++r) {                     // striped: coalesced over the frame's rows
+                    const int e = r * 32 + lane;
+                    klo[r] = e < n ? score_key(e) : 0xffffffffu;
+                    khi[r] = e + 1024 < n ? score_key(e + 1024) : 0xffffffffu;
+                }
+                warp_bitonic_sort2_u32<H>(klo, khi, lane);        // position = half*1024 + lane*32 + r
+#pragma unroll
+                for (int r = 0; r + 1 < H; ++r) {
+                    tie |= (klo[r] == klo[r + 1]) && (lane * H + r + 1 < n);
+                    tie |= (khi[r] == khi[r + 1]) && (1024 + lane * H + r + 1 < n);
+                }
+                const uint32_t nlo = __shfl_down_sync(FULL, klo[0], 1), nhi = __shfl_down_sync(FULL, khi[0], 1);
+                const uint32_t first_hi = __shfl_sync(FULL, khi[0], 0);
+                tie |= (lane < 31) && (klo[H - 1] == nlo) && ((lane + 1) * H < n);
+                tie |= (lane < 31) && (khi[H - 1] == nhi) && (1024 + (lane + 1) * H < n);
+                tie |= (lane == 31) && (klo[H - 1] == first_hi) && (1024 < n);
+#pragma unroll
+                for (int r = 0; r < H; ++r) {
+                    sk[lane * (H + 1) + r] = klo[r];                       // = skw(lane*32 + r)
+                    sk[1024 + 32 + lane * (H + 1) + r] = khi[r];           // = skw(1024 + lane*32 + r)
                 }
             }
-            // -- ties?  (equal adjacent keys among the n valid entries)
-            bool tie = false;
-            for (int q = lane; q + 1 < n; q += 32) tie |= (sk[q] == sk[q + 1]);
+            __syncwarp();
             const bool has_tie = __any_sync(FULL, tie);
             if (has_tie) {
                 for (int e = lane; e < n; e += 32) ct[e] = 0;
@@ -572,7 +589,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_frames_big_kernel(const NmsFr
                 uint32_t pos = 0;
                 for (int step = NPAD >> 1; step > 0; step >>= 1) {
                     const uint32_t q = pos + step - 1;
-                    if (q < (uint32_t)n && sk[q] < key) pos += step;
+                    if (q < (uint32_t)n && sk[skw((int)q)] < key) pos += step;
                 }
                 if (has_tie) {
                     // elements arrive in index order: the ordinal among equal keys is the running count
@@ -589,7 +606,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_frames_big_kernel(const NmsFr
             }
             __syncwarp();
             // -- invert: sk becomes the order (index at each sorted position)
-            for (int e = lane; e < n; e += 32) sk[rk[e]] = (uint32_t)e;
+            for (int e = lane; e < n; e += 32) sk[skw(rk[e])] = (uint32_t)e;
             __syncwarp();
 
             uint32_t rem0 = 0, rem1 = 0;
@@ -598,29 +615,53 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_frames_big_kernel(const NmsFr
             int32_t* out_idx = p.keep_idx + blk;
             uint8_t* out_m = p.keep_mask ? p.keep_mask + blk : nullptr;
             const unsigned lt = lanemask_lt();
+            // Greedy walk, 32 candidates of the score order per step, three phases per step so that no
+            // global load depends on another one of the same step:
+            //   1. every still-alive candidate gathers, from its own mask row, the bits of the later
+            //      alive candidates of the step (independent loads, 8 in flight per lane);
+            //   2. the step's greedy choice is resolved on those 32x32 bits in registers;
+            //   3. the rows of the kept boxes are ORed into the removed set (independent loads).
 #pragma unroll 1
             for (int g = 0; g < Wn; ++g) {
                 const bool valid = (g * 32 + lane) < n;
-                const uint32_t i = valid ? sk[g * 32 + lane] : 0u;
+                const uint32_t i = valid ? sk[skw(g * 32 + lane)] : 0u;
                 const int src = (int)((i >> 5) & 31);
                 const bool hi = ((i >> 5) & 32) != 0;
                 const uint32_t w0 = __shfl_sync(FULL, rem0, src), w1 = __shfl_sync(FULL, rem1, src);
-                unsigned alive = __ballot_sync(FULL, valid && !(((hi ? w1 : w0) >> (i & 31)) & 1u));
+                const unsigned alive = __ballot_sync(FULL, valid && !(((hi ? w1 : w0) >> (i & 31)) & 1u));
+                const bool me_alive = (alive >> lane) & 1u;
+                const uint32_t* myrow = gmask + (size_t)i * W;
+                uint32_t sup_set = 0;                 // bit l2: my box suppresses the candidate in lane l2 (> lane)
+                for (unsigned m = alive & (alive - 1); m;) {      // the first alive candidate is nobody's "later"
+                    int l2[8];
+                    uint32_t i2[8], w[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        l2[q] = m ? (__ffs(m) - 1) : 32;
+                        m &= m - 1;
+                        i2[q] = __shfl_sync(FULL, i, l2[q] & 31);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        w[q] = (me_alive && l2[q] > lane && l2[q] < 32) ? myrow[i2[q] >> 5] : 0u;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) sup_set |= ((w[q] >> (i2[q] & 31)) & 1u) << (l2[q] & 31);
+                }
                 unsigned kgrp = 0;
-                while (alive) {
-                    const int l = __ffs(alive) - 1;
+                for (unsigned a = alive; a;) {
+                    const int l = __ffs(a) - 1;
+                    kgrp |= (1u << l);
+                    a &= ~(1u << l);
+                    a &= ~__shfl_sync(FULL, sup_set, l);
+                }
+                for (unsigned m = kgrp; m; m &= m - 1) {
+                    const int l = __ffs(m) - 1;
                     const uint32_t ci = __shfl_sync(FULL, i, l);
                     if (check_zero)
                         zero_division_check_big(sk, n, sbox, sarea, rem0, rem1, ci, g * 32 + l, lane, p.status);
                     const uint32_t* row = gmask + (size_t)ci * W;
-                    const uint32_t r0 = (lane < Wn) ? row[lane] : 0u;
-                    const uint32_t r1 = (32 + lane < Wn) ? row[32 + lane] : 0u;
-                    rem0 |= r0;
-                    rem1 |= r1;
-                    kgrp |= (1u << l);
-                    const uint32_t v0 = __shfl_sync(FULL, r0, src), v1 = __shfl_sync(FULL, r1, src);
-                    alive &= ~__ballot_sync(FULL, ((hi ? v1 : v0) >> (i & 31)) & 1u);
-                    alive &= ~(1u << l);
+                    rem0 |= (lane < Wn) ? row[lane] : 0u;
+                    rem1 |= (32 + lane < Wn) ? row[32 + lane] : 0u;
                 }
                 const bool mine = (kgrp >> lane) & 1u;
                 if (mine) out_idx[cnt + __popc(kgrp & lt)] = srow[i];
@@ -641,7 +682,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_frames_big_kernel(const NmsFr
 
 static size_t big_smem_bytes(int nb, int npad) {
     return (size_t)nb * (sizeof(float4) + sizeof(float) + sizeof(int32_t)) + 256 * BIG_ST_LD * sizeof(uint32_t) +
-           (size_t)NMS_WARPS * npad * (sizeof(uint32_t) + 2 * sizeof(uint16_t));
+           (size_t)NMS_WARPS * (BIG_SK_LD * sizeof(uint32_t) + (size_t)npad * 2 * sizeof(uint16_t));
 }
 
 }  // namespace vdet

@@ -49,9 +49,9 @@ def new_status(device):
     return torch.zeros(1, dtype=torch.int32, device=device)
 
 
-def raise_for_status(status):
-    """Translate the device status word into the reference's Python exceptions (synchronises)."""
-    s = int(status.item()) & 0xffffffff
+def raise_for_status_word(word):
+    """Translate a status word already on the host into the reference's Python exceptions."""
+    s = int(word) & 0xffffffff
     if s & 0x80000000:
         raise RuntimeError("vdetlib_b200: internal frame-length mismatch")
     if s & _lib.STATUS_ZERO_DIVISION:
@@ -59,6 +59,11 @@ def raise_for_status(status):
     if s & _lib.STATUS_ALL_MISSING:
         raise IndexError("list index out of range")        # vdet/tubelet_cls.py:295
     return s
+
+
+def raise_for_status(status):
+    """Same for the device status word (synchronises)."""
+    return raise_for_status_word(status.item())
 
 
 def seg_offsets_uniform(n_frames, n_per_frame, device):

@@ -78,7 +78,7 @@ class VideoPostProcessor(object):
     same time.  Frame-major outputs make every chunk a contiguous byte range.
     """
 
-    def __init__(self, n_frames, n_boxes, n_classes, nms_thresh=0.3, device=None, n_chunks=4):
+    def __init__(self, n_frames, n_boxes, n_classes, nms_thresh=0.3, device=None, n_chunks=8):
         self.T, self.N, self.C = int(n_frames), int(n_boxes), int(n_classes)
         self.nms_thresh = float(nms_thresh)
         self.device = device or torch.device("cuda", torch.cuda.current_device())
@@ -100,6 +100,7 @@ class VideoPostProcessor(object):
         self.h_succ = torch.empty(rows, dtype=torch.int32).pin_memory()
         self.h_iou = torch.empty(rows, dtype=torch.float32).pin_memory()
         self.status = ops.new_status(dev)
+        self.h_status = torch.zeros(1, dtype=self.status.dtype).pin_memory()
         # frame ranges of the pipeline chunks
         n_chunks = max(1, min(int(n_chunks), T))
         edges = [round(k * T / n_chunks) for k in range(n_chunks + 1)]
@@ -158,27 +159,41 @@ class VideoPostProcessor(object):
         self.h_scores.copy_(torch.as_tensor(np.ascontiguousarray(scores, dtype=np.float32)).view(-1, self.C))
 
     def run_staged(self, halo=None, halo_fn=None):
-        """Pipelined H2D (pinned buffers) -> NMS per chunk -> D2H, then the link; synchronises and
-        returns host views.  ``halo_fn(d_first_frame_boxes)`` (optional) is called on the compute
-        stream once chunk 0 is on the device and returns the halo tensor (boundary exchange)."""
+        """Pipelined H2D (pinned buffers) -> link + NMS per chunk -> D2H; synchronises and returns
+        host views.  The boxes (4 floats/row) go first, so the link -- which needs no scores --
+        and its D2H run under the upload of the scores (C floats/row); each score chunk is
+        followed by its NMS launch and the download of its keep mask.  The step is bound by the
+        upload; what remains after its last byte is one chunk's NMS and mask download.
+        ``halo_fn(d_first_frame_boxes)`` (optional) is called on the compute stream once the
+        boxes are on the device and returns the halo tensor (boundary exchange)."""
         N, C = self.N, self.C
         cur = torch.cuda.current_stream()
         self.s_in.wait_stream(cur)
         self.s_out.wait_stream(cur)
         ev_in = []
         with torch.cuda.stream(self.s_in):
+            self.d_boxes.copy_(self.h_boxes, non_blocking=True)
+            ev_boxes = torch.cuda.Event()
+            ev_boxes.record(self.s_in)
             for f0, f1 in self.chunks:
                 r0, r1 = f0 * N, f1 * N
-                self.d_boxes[r0:r1].copy_(self.h_boxes[r0:r1], non_blocking=True)
                 self.d_scores[r0:r1].copy_(self.h_scores[r0:r1], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self.s_in)
                 ev_in.append(ev)
+        cur.wait_event(ev_boxes)
+        if halo_fn is not None:
+            halo = halo_fn(self.d_boxes[:N])
+        ops.link_frames(self.d_boxes, self.seg_offsets, N, halo, out=(self.d_succ, self.d_iou))
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.s_out.wait_event(ev)
+        with torch.cuda.stream(self.s_out):
+            self.h_succ.copy_(self.d_succ, non_blocking=True)
+            self.h_iou.copy_(self.d_iou, non_blocking=True)
         for k, (f0, f1) in enumerate(self.chunks):
             r0, r1 = f0 * N, f1 * N
             cur.wait_event(ev_in[k])
-            if k == 0 and halo_fn is not None:
-                halo = halo_fn(self.d_boxes[:N])
             ops.nms_frames(self.d_boxes[r0:r1], self.d_scores[r0:r1], self.chunk_seg[f1 - f0], self.nms_thresh, N,
                            want_mask=True, status=self.status, frame_major_out=True,
                            out=(self.d_idx[r0 * C:r1 * C], self.d_cnt[f0:f1], self.d_mask[r0 * C:r1 * C]))
@@ -188,12 +203,10 @@ class VideoPostProcessor(object):
             with torch.cuda.stream(self.s_out):
                 self.h_mask[r0 * C:r1 * C].copy_(self.d_mask[r0 * C:r1 * C], non_blocking=True)
                 self.h_cnt[f0:f1].copy_(self.d_cnt[f0:f1], non_blocking=True)
-        succ, link_iou = ops.link_frames(self.d_boxes, self.seg_offsets, N, halo)
-        self.h_succ.copy_(succ, non_blocking=True)
-        self.h_iou.copy_(link_iou, non_blocking=True)
-        cur.wait_stream(self.s_out)
-        cur.synchronize()
-        ops.raise_for_status(self.status)
+        with torch.cuda.stream(self.s_out):
+            self.h_status.copy_(self.status, non_blocking=True)
+        self.s_out.synchronize()
+        ops.raise_for_status_word(int(self.h_status.item()))
         return {"keep_mask": self.h_mask.numpy().reshape(self.T, C, N), "keep_cnt": self.h_cnt.numpy(),
                 "succ": self.h_succ.numpy(), "link_iou": self.h_iou.numpy()}
 
