@@ -38,6 +38,7 @@ struct NmsFramesParams {
     uint32_t* gmask;   // big-frame variant: per-CTA bit-matrix slots in global memory
     int npad;          // big-frame variant: power-of-two sort length >= nb
     int fast_filter;   // 1: division-free threshold filter allowed (2^-20 <= T <= 2)
+    float thresh_hi, thresh_lo;   // T(1 +- 2^-21) for that filter
     int so_words;      // per-warp order scratch: (nb/32)*33 words
     int frame_major;   // output layout (VDET_LAYOUT_*)
     // work items: frames [0, split_from) are one item each; every later frame is cut into `nsplit`
@@ -46,26 +47,45 @@ struct NmsFramesParams {
     int split_from, nsplit, n_items;
 };
 
+// 32x32 bit-matrix transpose across the warp (lane = row): five block-swap steps, each one
+// shuffle + shift + bit-select.  out[L] bit r == in[r] bit L.
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, const int lane) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        const uint32_t m = (s == 16) ? 0x0000ffffu : (s == 8) ? 0x00ff00ffu : (s == 4) ? 0x0f0f0f0fu
+                         : (s == 2) ? 0x33333333u : 0x55555555u;     // positions with bit s clear
+        const uint32_t y = __shfl_xor_sync(FULL, x, s);
+        const bool upper = (lane & s) == 0;
+        const uint32_t t = upper ? (y << s) : (y >> s);
+        const uint32_t keep = upper ? m : ~m;
+        x = (x & keep) | (t & ~keep);
+    }
+    return x;
+}
+
 // One 32x32 tile of the suppression bit matrix: lane = row i (box in registers), the 32 columns
 // of block `cb` are broadcast from shared memory.  Returns this lane's word for row i and, in
-// `tword`, the transposed word (row cb*32+lane, columns = this row block) collected from
-// ballots -- IoU is symmetric bit for bit (max/min/add commute), so only tiles with cb >= rb are
-// evaluated.
+// `tword`, the transposed word (row cb*32+lane, columns = this row block) -- IoU is symmetric
+// bit for bit (max/min/add commute), so only tiles with cb >= rb are evaluated.
 //
 // FAST: the threshold test avoids the IEEE division.  fl(inter/uni) >= T holds iff
-// inter/uni >= m for a midpoint m in (T(1-2^-24), T]; with p = fl(T*uni) (relative error
-// <= 2^-24): inter > p(1+2^-21) proves the test true, inter < p(1-2^-21) proves it false.  Pairs
-// in between (or with uni <= 0 / NaN) set `uncertain`, and the caller redoes the tile with the
-// exact division (FAST = false).  Results are identical to the exact path by construction.
-// The host enables FAST only for 2^-20 <= T <= 2, and unions outside (1e-30, 1e30) are
-// "uncertain", so T*uni can neither overflow nor go subnormal.
-template <bool FAST>
+// inter/uni >= m for a midpoint m in [T(1-2^-24), T].  With Thi = fl(T(1+2^-21)) and
+// Tlo = fl(T(1-2^-21)) (host, any rounding): inter > fl(Thi*uni) >= T*uni(1+2^-21)(1-2^-24)^2
+// > T*uni proves the test true; inter < fl(Tlo*uni) <= T*uni(1-2^-21)(1+2^-24)^2 < T(1-2^-24)*uni
+// proves it false.  Pairs in between (or with uni <= 0 / NaN) set `uncertain`, and the caller
+// redoes the tile with the exact division (FAST = false).  Results are identical to the exact
+// path by construction.  The host enables FAST only for 2^-20 <= T <= 2, and unions outside
+// (1e-30, 1e30) are "uncertain", so T*uni can neither overflow nor go subnormal.
+// SANE (CTA-uniform: every box of the frame passes box_sane): unions lie in [2^-48, 2^43] and are
+// never zero (uni >= the larger area, rounding is monotone), so the range and zero tests go.
+template <bool FAST, bool SANE>
 __device__ __forceinline__ uint32_t mask_tile(const float4 bi, const float ai, const float4* __restrict__ sbox,
                                               const float* __restrict__ sarea, const int cb, const float T,
+                                              const float Thi, const float Tlo,
                                               const int lane, uint32_t& tword, bool& zero, bool& uncertain) {
-    uint32_t word = 0, tw = 0;
+    uint32_t word = 0;
     bool z = false, unc = false;
-#pragma unroll 8
+#pragma unroll
     for (int jj = 0; jj < 32; ++jj) {
         const int j = cb * 32 + jj;
         const float4 bj = sbox[j];
@@ -74,23 +94,33 @@ __device__ __forceinline__ uint32_t mask_tile(const float4 bi, const float ai, c
         inter_union_f32(bi, ai, bj, aj, inter, uni);
         bool sup;
         if (FAST) {
-            const float pth = __fmul_rn(T, uni);
-            const float hi = __fmaf_rn(pth, 4.76837158203125e-07f, pth);     // p * (1 + 2^-21)
-            const float lo = __fmaf_rn(pth, -4.76837158203125e-07f, pth);    // p * (1 - 2^-21)
-            sup = inter > hi;
-            unc |= !(sup || inter < lo) || !(uni > 1e-30f && uni < 1e30f);
+            sup = inter > __fmul_rn(Thi, uni);
+            unc |= !sup && !(inter < __fmul_rn(Tlo, uni));
+            if (!SANE) unc |= !(uni > 1e-30f && uni < 1e30f);
         } else {
             sup = iou_ge(inter, uni, T);
         }
-        z |= (uni == 0.0f);
+        if (!SANE) z |= (uni == 0.0f);
         if (sup) word |= (1u << jj);
-        const unsigned b = __ballot_sync(FULL, sup);
-        if (lane == jj) tw = b;
     }
-    tword = tw;
+    tword = warp_transpose32(word, lane);
     zero = z;
     uncertain = unc;
     return word;
+}
+
+// The tile with the cheapest admissible test; an uncertain pair anywhere redoes it exactly.
+template <bool SANE>
+__device__ __forceinline__ uint32_t mask_tile_auto(const bool fast, const float4 bi, const float ai,
+                                                   const float4* __restrict__ sbox, const float* __restrict__ sarea,
+                                                   const int cb, const float T, const float Thi, const float Tlo,
+                                                   const int lane, uint32_t& tword, bool& zero) {
+    bool unc;
+    if (fast) {
+        const uint32_t word = mask_tile<true, SANE>(bi, ai, sbox, sarea, cb, T, Thi, Tlo, lane, tword, zero, unc);
+        if (!__any_sync(FULL, unc)) return word;
+    }
+    return mask_tile<false, false>(bi, ai, sbox, sarea, cb, T, Thi, Tlo, lane, tword, zero, unc);
 }
 
 // Exact ZeroDivisionError test of nms.pyx:64 (cold path, only for frames that contain a
@@ -153,6 +183,7 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 3 : 1)) nms_frames_
         }
         // ---- A: stage boxes, areas, original row ids (and scores) ------------------------
         if (tid == 0) s_zero_union = 0;
+        bool all_sane = true;
         for (int e = tid; e < NB; e += NMS_THREADS) {
             float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
             int32_t row = -1;
@@ -163,8 +194,9 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 3 : 1)) nms_frames_
             sbox[e] = b;
             sarea[e] = area_f32(b);
             srow[e] = row;
+            all_sane &= box_sane(b);
         }
-        __syncthreads();
+        const bool sane = __syncthreads_and(all_sane) != 0;     // CTA-uniform: cheaper pair test
         if (p.stage) {
             if (p.row_ids == nullptr && p.score_ldc == 1 && p.score_ldr == C) {
                 // contiguous [n, C] block: flat coalesced read, transposed conflict-free write
@@ -196,15 +228,11 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 3 : 1)) nms_frames_
                     const float4 bi = sbox[i];
                     const float ai = sarea[i];
                     uint32_t tword;
-                    bool zero, unc;
-                    uint32_t word;
-                    if (p.fast_filter) {
-                        word = mask_tile<true>(bi, ai, sbox, sarea, cb, T, lane, tword, zero, unc);
-                        if (__any_sync(FULL, unc))   // a pair too close to the threshold: exact redo
-                            word = mask_tile<false>(bi, ai, sbox, sarea, cb, T, lane, tword, zero, unc);
-                    } else {
-                        word = mask_tile<false>(bi, ai, sbox, sarea, cb, T, lane, tword, zero, unc);
-                    }
+                    bool zero;
+                    const uint32_t word0 =
+                        sane ? mask_tile_auto<true>(p.fast_filter, bi, ai, sbox, sarea, cb, T, p.thresh_hi, p.thresh_lo, lane, tword, zero)
+                             : mask_tile_auto<false>(p.fast_filter, bi, ai, sbox, sarea, cb, T, p.thresh_hi, p.thresh_lo, lane, tword, zero);
+                    uint32_t word = word0;
                     // columns / rows beyond the frame never suppress and are never visited
                     const int cvalid = n - cb * 32, rvalid = n - rb * 32;
                     if (cvalid < 32) word &= (1u << cvalid) - 1u;
@@ -468,6 +496,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_frames_big_kernel(const NmsFr
             continue;
         }
         if (tid == 0) s_zero_union = 0;
+        bool all_sane = true;
         for (int e = tid; e < NB; e += NMS_THREADS) {
             float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
             int32_t row = -1;
@@ -478,8 +507,9 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_frames_big_kernel(const NmsFr
             sbox[e] = b;
             sarea[e] = area_f32(b);
             srow[e] = row;
+            all_sane &= box_sane(b);
         }
-        __syncthreads();
+        const bool sane = __syncthreads_and(all_sane) != 0;     // CTA-uniform: cheaper pair test
         const int Wn = (n + 31) >> 5;
         // ---- B: bit matrix, 256x256 super tiles of the upper triangle ------------------------
         {
@@ -498,14 +528,9 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_frames_big_kernel(const NmsFr
                             const int cb = Cc * 8 + cbl;
                             uint32_t word = 0, tword = 0;
                             if (cb < Wn) {
-                                bool zero, unc;
-                                if (p.fast_filter) {
-                                    word = mask_tile<true>(bi, ai, sbox, sarea, cb, T, lane, tword, zero, unc);
-                                    if (__any_sync(FULL, unc))
-                                        word = mask_tile<false>(bi, ai, sbox, sarea, cb, T, lane, tword, zero, unc);
-                                } else {
-                                    word = mask_tile<false>(bi, ai, sbox, sarea, cb, T, lane, tword, zero, unc);
-                                }
+                                bool zero;
+                                word = sane ? mask_tile_auto<true>(p.fast_filter, bi, ai, sbox, sarea, cb, T, p.thresh_hi, p.thresh_lo, lane, tword, zero)
+                                            : mask_tile_auto<false>(p.fast_filter, bi, ai, sbox, sarea, cb, T, p.thresh_hi, p.thresh_lo, lane, tword, zero);
                                 any_zero |= zero;
                                 const int cvalid = n - cb * 32, rvalid = n - rb * 32;
                                 if (cvalid < 32) word &= (1u << cvalid) - 1u;
@@ -722,6 +747,8 @@ extern "C" int vdet_nms_frames_f32(const float* boxes, int box_ld,
     {
         const float Tf = thresh_ceil_f32(thresh);
         p.fast_filter = (Tf >= 9.5367431640625e-07f && Tf <= 2.0f) ? 1 : 0;
+        p.thresh_hi = (float)((double)Tf * (1.0 + 4.76837158203125e-07));
+        p.thresh_lo = (float)((double)Tf * (1.0 - 4.76837158203125e-07));
     }
     p.boxes = boxes; p.box_ld = box_ld;
     p.box_vec = (box_ld == 4) && ((reinterpret_cast<uintptr_t>(boxes) & 15) == 0);
