@@ -69,6 +69,11 @@ int         vdet_sm_count(int device);
  * collective with them reserves a few SMs so that the collective's kernel can be scheduled at
  * once instead of waiting for the persistent grid to drain (process-wide setting, default 0). */
 int         vdet_set_reserved_sms(int n);
+/* Host-side staging copy into a pinned upload buffer with non-temporal (streaming) stores.
+ * A buffer filled with ordinary stores sits dirty in the CPU caches and the GPU's DMA reads of it
+ * run at about half the PCIe rate on the measured host (profiles/r01_pcie.md); streamed lines are
+ * in DRAM when the copy engine asks for them.  Plain host memory in and out, no CUDA call. */
+int         vdet_host_copy_stream(void* dst, const void* src, size_t bytes);
 
 /* ---------------------------------------------------------------------------------------
  * Per-frame greedy NMS on class-shared boxes.

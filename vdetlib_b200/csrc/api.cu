@@ -3,6 +3,8 @@
 #include <string.h>
 
 #include "common.cuh"
+#include <emmintrin.h>
+#include <cstring>
 
 namespace vdet {
 
@@ -59,6 +61,34 @@ extern "C" {
 int vdet_abi_version(void) { return VDET_ABI_VERSION; }
 
 const char* vdet_last_error(void) { return vdet::g_err; }
+
+int vdet_host_copy_stream(void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return VDET_OK;
+    if (dst == nullptr || src == nullptr) {
+        vdet::set_error("host_copy_stream: null pointer");
+        return VDET_ERR_INVALID;
+    }
+    unsigned char* d = static_cast<unsigned char*>(dst);
+    const unsigned char* s = static_cast<const unsigned char*>(src);
+    size_t head = (16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15;     // stores must be 16-byte aligned
+    if (head > bytes) head = bytes;
+    memcpy(d, s, head);
+    d += head; s += head; bytes -= head;
+    const size_t nvec = bytes / 16;
+    __m128i* dv = reinterpret_cast<__m128i*>(d);
+    const __m128i* sv = reinterpret_cast<const __m128i*>(s);
+    size_t i = 0;
+    for (; i + 4 <= nvec; i += 4) {                                      // one 64-byte line per round
+        const __m128i a = _mm_loadu_si128(sv + i), b = _mm_loadu_si128(sv + i + 1);
+        const __m128i c = _mm_loadu_si128(sv + i + 2), e = _mm_loadu_si128(sv + i + 3);
+        _mm_stream_si128(dv + i, a); _mm_stream_si128(dv + i + 1, b);
+        _mm_stream_si128(dv + i + 2, c); _mm_stream_si128(dv + i + 3, e);
+    }
+    for (; i < nvec; ++i) _mm_stream_si128(dv + i, _mm_loadu_si128(sv + i));
+    memcpy(d + nvec * 16, s + nvec * 16, bytes - nvec * 16);
+    _mm_sfence();
+    return VDET_OK;
+}
 
 int vdet_set_reserved_sms(int n) {
     vdet::set_reserved_sms(n);
