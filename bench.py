@@ -318,7 +318,7 @@ def run_b200(args):
     # of traffic), so the end-to-end steady state needs more than W warm-up steps: warm up until the
     # step time stops improving (bounded), report how many steps that took, then time exactly K steps.
     pp.pp.stage(*host0)
-    e2e_warm, prev = 0, None
+    e2e_warm, prev, ramp = 0, None, []
     while e2e_warm < 400:
         w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0.record()
@@ -328,6 +328,7 @@ def run_b200(args):
         torch.cuda.synchronize()
         e2e_warm += max(W, 20)
         t = max_over_ranks(w0.elapsed_time(w1))
+        ramp.append(round(t / max(W, 20), 3))
         if prev is not None and t > 0.97 * prev and e2e_warm >= 60:
             break
         prev = t
@@ -341,7 +342,7 @@ def run_b200(args):
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / K
     e2e = {"value": world * T * N / (e2e_ms / 1000.0), "unit": "boxes/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": pp.pp.h2d_bytes, "d2h_bytes_per_step": pp.pp.d2h_bytes,
-           "warmup_steps": e2e_warm,
+           "warmup_steps": e2e_warm, "warmup_ms_per_step": ramp,
            "pcie_GBs": (pp.pp.h2d_bytes + pp.pp.d2h_bytes) / (e2e_ms / 1000.0) / 1e9,
            "api": "vdetlib_b200.dist.ShardedVideoPostProcessor.step_host (pinned host buffers)"}
     assert int(res["keep_cnt"].sum()) > 0

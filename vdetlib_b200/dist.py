@@ -64,7 +64,7 @@ class ShardedVideoPostProcessor(object):
     """The per-rank step of the multi-GPU pipeline: NMS of the local frames, boundary exchange,
     link (local frames + halo).  Weak scaling: every rank holds ``n_frames`` frames."""
 
-    def __init__(self, n_frames, n_boxes, n_classes, nms_thresh=0.3, device=None, group=None, n_chunks=4):
+    def __init__(self, n_frames, n_boxes, n_classes, nms_thresh=0.3, device=None, group=None, n_chunks=8):
         from .vdet.video_det import VideoPostProcessor
         self.pp = VideoPostProcessor(n_frames, n_boxes, n_classes, nms_thresh, device, n_chunks=n_chunks)
         self.exchange = BoundaryExchange(n_boxes, self.pp.device, group)
@@ -108,7 +108,7 @@ class ShardedVideoPostProcessor(object):
         """The end-to-end step: pipelined H2D from the pinned staging buffers (fill them with
         ``self.pp.stage(boxes, scores)``), kernels + boundary exchange, D2H of the results."""
         pp = self.pp
-        res = pp.run_staged(halo_fn=self._halo_then_join)
+        res = pp.run_staged(halo_fn=self._halo_then_join if self.exchange.world > 1 else None)
         return res
 
     def _halo_then_join(self, d_first_frame):
