@@ -290,6 +290,50 @@ def test_frame_major_layout_and_pipelined_postprocessor():
             assert np.array_equal(g_out["succ"].cpu().numpy(), out["succ"])
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_video_postprocessor_two_steps_in_flight(graph):
+    """submit_staged / collect: two double-buffered steps in flight, restaged inputs in between,
+    eager stream pipeline and whole-step CUDA-graph replay -- same results as the oracle every time."""
+    from vdetlib_b200.vdet.video_det import VideoPostProcessor
+    T, N, C = 12, 150, 7
+    pp = VideoPostProcessor(T, N, C, 0.3, n_chunks=4)
+    data = [synth.boxes_scores(T, N, C, seed=300 + k) for k in range(3)]
+    want = []
+    for b, s in data:
+        km, _, kc = c_oracle.nms_frames(b, s, 0.3)
+        ls, lb = c_oracle.link_f32(b)
+        want.append((km, kc, ls, lb))
+
+    def check(out, w):
+        km, kc, ls, lb = w
+        assert np.array_equal(out["keep_mask"], km) and np.array_equal(out["keep_cnt"], kc)
+        got = out["succ"][:(T - 1) * N].reshape(T - 1, N) - np.arange(1, T)[:, None] * N
+        assert np.array_equal(got, ls)
+        assert np.array_equal(out["link_iou"][:(T - 1) * N].reshape(T - 1, N), lb)
+
+    for rnd in range(3):                                     # slots alternate: 0,1 | 0,1 | 0,1
+        b, s = data[rnd]
+        pp.stage(b, s)
+        t0 = pp.submit_staged(graph=graph)
+        t1 = pp.submit_staged(graph=graph)                   # same staged inputs, the other slot
+        with pytest.raises(RuntimeError):
+            pp.submit_staged(graph=graph)                    # both slots busy
+        with pytest.raises(RuntimeError):
+            pp.stage(b, s)                                   # in-flight steps still read the staging buffers
+        check(pp.collect(t0), want[rnd])
+        # keep the pipeline full: a third step goes out before the second is collected
+        t2 = pp.submit_staged(graph=graph)
+        check(pp.collect(t1), want[rnd])
+        check(pp.collect(t2), want[rnd])
+        with pytest.raises(RuntimeError):
+            pp.collect(t2)
+    # the synchronous call still works afterwards, on slot 0, mixed with the device entry
+    out = pp.run_host(*data[0])
+    check(out, want[0])
+    dev_out = pp.run_device(pp.d_boxes, pp.d_scores)
+    assert np.array_equal(dev_out["keep_mask"].cpu().numpy(), want[0][0])
+
+
 def test_sort_by_score_desc():
     rng = np.random.default_rng(6)
     for n in (1, 5, 2048, 2049, 100000):

@@ -104,12 +104,22 @@ class ShardedVideoPostProcessor(object):
         res.update(succ=succ, link_iou=link_iou)
         return res
 
-    def step_host(self):
-        """The end-to-end step: pipelined H2D from the pinned staging buffers (fill them with
-        ``self.pp.stage(boxes, scores)``), kernels + boundary exchange, D2H of the results."""
-        pp = self.pp
-        res = pp.run_staged(halo_fn=self._halo_then_join if self.exchange.world > 1 else None)
-        return res
+    def step_host(self, graph=False):
+        """The end-to-end step, synchronous: pipelined H2D from the pinned staging buffers (fill them
+        with ``self.pp.stage(boxes, scores)``), kernels + boundary exchange, D2H of the results."""
+        return self.collect(self.submit_host(graph))
+
+    def submit_host(self, graph=False):
+        """Enqueue one end-to-end step without waiting for it; returns a ticket for :meth:`collect`.
+        Two steps may be in flight (double-buffered device and result buffers), which keeps the
+        host->device link busy across step boundaries.  ``graph`` (single rank only): replay the
+        step from one CUDA graph."""
+        multi = self.exchange.world > 1
+        return self.pp.submit_staged(halo_fn=self._halo_then_join if multi else None, graph=graph and not multi)
+
+    def collect(self, ticket):
+        """Wait for a submitted step; host views of its results (valid until the slot is reused)."""
+        return self.pp.collect(ticket)
 
     def _halo_then_join(self, d_first_frame):
         halo = self._exchange(d_first_frame)
