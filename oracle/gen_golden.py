@@ -204,5 +204,57 @@ def main():
     print("golden vectors written to", OUT)
 
 
+def det_mat_case():
+    """Inputs of the raw-detection loader golden: a vid proto and, per frame, what its .mat file holds
+    (None = no file).  Covers: ``<basename>.mat`` vs ``<path>.mat`` lookup, a frame without boxes, a
+    missing file, float32 ('single') and float64 arrays, frames listed out of order."""
+    rng = np.random.default_rng(5000)
+    vid = {'video': 'golden_mat', 'root_path': '/nowhere',
+           'frames': [{'frame': f, 'path': '%06d.JPEG' % f} for f in (1, 2, 3, 5, 4, 6)]}
+    C = 4
+    mats = {}
+    for f, n, dt, by_path in ((1, 7, np.float64, False), (2, 0, np.float64, False), (3, 5, np.float32, True),
+                              (4, 1, np.float64, False), (5, 9, np.float32, False)):
+        boxes = np.round(rng.uniform(0, 600, (n, 4))).astype(dt) + (0.25 if dt is np.float32 else 0.0)
+        zs = rng.normal(0, 2, (n, C)).astype(dt)
+        mats[f] = (boxes, zs, by_path)
+    return vid, mats                                    # frame 6: no file at all
+
+
+def write_det_mats(vid, mats, det_dir):
+    import scipy.io as sio
+    for fr in vid['frames']:
+        if fr['frame'] not in mats:
+            continue
+        boxes, zs, by_path = mats[fr['frame']]
+        name = (fr['path'] if by_path else os.path.splitext(fr['path'])[0]) + '.mat'
+        sio.savemat(os.path.join(det_dir, name), {'boxes': boxes, 'zs': zs})
+
+
+def main_det_mat():
+    """tests/golden/det_mat.npz: the reference's load_det_info / load_frame_to_det
+    (utils/protocol.py:528-555) on .mat files written from det_mat_case()."""
+    import tempfile
+    build_ref.build()
+    R = ref_py2.RefFunctions(build_ref.load())
+    vid, mats = det_mat_case()
+    g = {}
+    with tempfile.TemporaryDirectory() as d:
+        write_det_mats(vid, mats, d)
+        info = R.load_det_info(vid, d)
+        f2d = R.load_frame_to_det(vid, d)
+    g["det_info"] = np.asarray(info)
+    g["frames_with_file"] = np.asarray(sorted(f2d), np.int64)
+    for f, (b, z) in f2d.items():
+        g["f2d_boxes_%d" % f] = b
+        g["f2d_zs_%d" % f] = z
+    np.savez_compressed(os.path.join(OUT, "det_mat.npz"), **g)
+    print("det_mat golden written:", g["det_info"].shape, g["frames_with_file"])
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "det_mat":
+        main_det_mat()
+    else:
+        main()
+        main_det_mat()

@@ -94,7 +94,7 @@ class RefFunctions(object):
         ("utils/protocol.py", ["det_score", "top_detections", "frame_top_detections",
                                "tubelets_proto_from_tracks_proto", "tubelets_overlap",
                                "merge_score_protos", "tracks_proto_from_boxes",
-                               "score_proto"]),
+                               "score_proto", "load_frame_to_det", "load_det_info"]),
         ("vdet/video_det.py", ["apply_vid_nms"]),
         ("vdet/image_det.py", ["apply_image_nms"]),
         ("vdet/tubelet_cls.py", ["do_score_completion", "dets_spatial_max_pooling",
@@ -116,6 +116,7 @@ class RefFunctions(object):
         with open(os.path.join(REF_ROOT, "misc", "imagenet_vdet_classes.txt")) as f:
             classes = [line.strip() for line in f.readlines()]        # utils/common.py:28-35
         from scipy.interpolate import interp1d
+        import scipy.io as sio
         import hashlib
 
         def bbox_hash(video_name, frame_id, bbox):                       # utils/protocol.py:372-375 (py3 bytes)
@@ -124,7 +125,7 @@ class RefFunctions(object):
 
         ns = {
             "np": np, "copy": copy, "defaultdict": defaultdict, "itemgetter": itemgetter,
-            "logging": quiet, "interp1d": interp1d,
+            "logging": quiet, "interp1d": interp1d, "os": os, "sio": sio,
             "imagenet_vdet_classes": classes, "bbox_hash": bbox_hash,
             "nms": cython_nms.nms, "vid_nms": cython_nms.vid_nms,
             "track_det_nms": cython_nms.track_det_nms,

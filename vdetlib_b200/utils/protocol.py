@@ -1,8 +1,9 @@
 """Protocol-dict helpers the hot-path adapters need (reference utils/protocol.py).
 
 The proto schemas (vid / box / det / track / score / annot, utils/protocol.py:7-192) are kept
-verbatim: plain JSON-style dicts.  Only the helpers on the hot path are provided; JSON / .mat
-file I/O is host-side and out of scope.
+verbatim: plain JSON-style dicts.  Only the helpers on the hot path are provided.  File I/O:
+``proto_load`` / ``proto_dump`` as in the reference (JSON, transparent gzip) plus the packed
+binary container of ``vdetlib_b200.utils.packed`` for paths ending in ``.vdetpk``.
 """
 import copy
 import gzip
@@ -15,7 +16,14 @@ from ..vdet.dataset import imagenet_vdet_classes
 
 
 def proto_load(file_path):
-    """utils/protocol.py:209-220 (transparent .gz)."""
+    """utils/protocol.py:209-220 (transparent .gz).  A ``.vdetpk`` path -- or a ``.vdetpk`` side-car
+    next to the JSON file, preferred like the reference prefers ``.gz`` -- is read from the packed
+    container instead of being parsed as JSON."""
+    if os.path.splitext(file_path)[1] != '.vdetpk' and os.path.isfile(file_path + '.vdetpk'):
+        file_path += '.vdetpk'
+    if os.path.splitext(file_path)[1] == '.vdetpk':
+        from .packed import proto_load_packed
+        return proto_load_packed(file_path)
     if os.path.isfile(file_path + '.gz'):
         file_path += '.gz'
     if os.path.splitext(file_path)[1] == '.gz':
@@ -26,7 +34,10 @@ def proto_load(file_path):
 
 
 def proto_dump(obj, file_path):
-    """utils/protocol.py:223-236."""
+    """utils/protocol.py:223-236; ``.vdetpk`` paths are written as the packed container."""
+    if os.path.splitext(file_path)[1] == '.vdetpk':
+        from .packed import proto_dump_packed
+        return proto_dump_packed(obj, file_path)
     if os.path.splitext(file_path)[1] == '.gz':
         with gzip.open(file_path, 'wt', compresslevel=1) as f:
             json.dump(obj, f, indent=2)
