@@ -283,6 +283,7 @@ def run_b200(args):
         dom, dom_ms, dom_bytes = "link_frames_kernel", ms_link, bytes_link
     achieved = dom_bytes / (dom_ms / 1000.0) / 1e9
     traffic = None            # dram read+write of that kernel from the committed ncu --set full capture
+    warp_inst = None          # and its executed warp instructions (same capture), for the issue roofline
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu.json")))["kernels"]
         for name, caps in prof.items():
@@ -290,6 +291,7 @@ def run_b200(args):
                 scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
                 traffic = (caps[0]["dram_read"] * scale.get(caps[0]["dram_read_unit"], 1.0) +
                            caps[0]["dram_write"] * scale.get(caps[0]["dram_write_unit"], 1.0))
+                warp_inst = caps[0].get("warp_instructions")
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
@@ -299,6 +301,18 @@ def run_b200(args):
                 "note": "the step's kernels are issue/latency bound (sort + greedy walk + N^2 pair IoUs per "
                         "frame), not HBM bound; see DESIGN.md. The HBM-roofline kernel of BASELINE.json is "
                         "iou_matrix_f32 (below)."}
+    if warp_inst:
+        # what actually bounds the dominant kernel: warp-instruction issue.  Peak = SMs x 4 schedulers x
+        # 1 warp instruction per clock at the maximum SM clock; instructions per launch from the
+        # committed ncu capture (smsp__inst_executed.sum), duration measured live above.
+        props = torch.cuda.get_device_properties(dev)
+        sm_hz = 1e6 * float(props.clock_rate) / 1e3 if getattr(props, "clock_rate", 0) else 1.965e9
+        issue_peak = props.multi_processor_count * 4 * sm_hz
+        roofline["issue"] = {"warp_instructions_per_launch": warp_inst,
+                             "achieved_warp_inst_per_s": warp_inst / (dom_ms / 1000.0),
+                             "peak_warp_inst_per_s": issue_peak, "frac": warp_inst / (dom_ms / 1000.0) / issue_peak,
+                             "sm_count": props.multi_processor_count, "sm_clock_hz": sm_hz,
+                             "source": "profiles/r01_ncu.json (ncu --set full of this kernel) / live CUDA-event time"}
 
     # ---- the IoU-matrix kernel against HBM (BASELINE.json: "% HBM peak on IoU kernel") -----
     A = 16384

@@ -145,7 +145,9 @@ __device__ __noinline__ void zero_division_check(const uint32_t* so, int ngroups
     if (__any_sync(FULL, zd) && lane == 0) atomicOr(status, VDET_STATUS_ZERO_DIVISION);
 }
 
-template <int NPER>
+// STAGE: the frame's scores are transposed into shared memory (as sort keys) in phase A; a
+// compile-time switch, so the per-element key fetch carries no trace of the other path.
+template <int NPER, bool STAGE>
 __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 3 : 1)) nms_frames_kernel(const NmsFramesParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NB = p.nb;
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 3 : 1)) nms_frames_
     int32_t* srow = reinterpret_cast<int32_t*>(sarea + NB);
     uint32_t* smask = reinterpret_cast<uint32_t*>(srow + NB);
     uint32_t* sord = smask + (size_t)NB * WS;                       // [NMS_WARPS][so_words] order scratch
-    float* sscore = reinterpret_cast<float*>(sord + NMS_WARPS * p.so_words);
+    uint32_t* sscore = sord + NMS_WARPS * p.so_words;             // staged scores, already as sort keys
     __shared__ int s_zero_union;
 
     const int tid = threadIdx.x;
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 3 : 1)) nms_frames_
             all_sane &= box_sane(b);
         }
         const bool sane = __syncthreads_and(all_sane) != 0;     // CTA-uniform: cheaper pair test
-        if (p.stage) {
+        if (STAGE) {
             if (p.row_ids == nullptr && p.score_ldc == 1 && p.score_ldr == C) {
                 // contiguous [n, C] block: flat coalesced read, transposed conflict-free write
                 const float* src = p.scores + (int64_t)off * C;
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 3 : 1)) nms_frames_
                 int r = tid / C, c = tid - r * C;                  // one division, then incremental
                 const int dr = NMS_THREADS / C, dc = NMS_THREADS - dr * C;
                 for (int f = tid; f < total; f += NMS_THREADS) {
-                    sscore[c * SST + r] = __ldg(src + f);
+                    sscore[c * SST + r] = f32_key_desc(__ldg(src + f));
                     r += dr; c += dc;
                     if (c >= C) { c -= C; ++r; }
                 }
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 3 : 1)) nms_frames_
                 const int total = n * C;
                 for (int f = tid; f < total; f += NMS_THREADS) {
                     const int r = f / C, c = f - r * C;
-                    sscore[c * SST + r] = __ldg(p.scores + (int64_t)srow[r] * p.score_ldr + (int64_t)c * p.score_ldc);
+                    sscore[c * SST + r] = f32_key_desc(__ldg(p.scores + (int64_t)srow[r] * p.score_ldr + (int64_t)c * p.score_ldc));
                 }
             }
         }
@@ -252,11 +254,10 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 3 : 1)) nms_frames_
         uint32_t* so = sord + warp * p.so_words;          // this warp's order scratch (skewed)
         const int cap = Wn * 32;                          // sorted positions >= cap are padding
         for (int c = c_begin + warp; c < c_end; c += NMS_WARPS) {
-            const float* sc_smem = sscore + c * SST;
+            const uint32_t* sc_smem = sscore + c * SST;
             const float* sc_glob = p.scores + (int64_t)c * p.score_ldc;
             auto score_key = [&](const int e) -> uint32_t {
-                const float sv = p.stage ? sc_smem[e] : __ldg(sc_glob + (int64_t)srow[e] * p.score_ldr);
-                return f32_key_desc(sv);
+                return STAGE ? sc_smem[e] : f32_key_desc(__ldg(sc_glob + (int64_t)srow[e] * p.score_ldr));
             };
             // -- order: so[skew(pos)] = index of the pos-th highest score (ties: lower index first).
             // Fast path: sort the 32-bit score keys alone, then every element finds its rank by
@@ -284,26 +285,40 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 3 : 1)) nms_frames_
                         if (pp < cap) so[pp + (pp >> 5)] = k32[r];
                     }
                     __syncwarp();
-                    uint32_t rank[NPER];
+                    // Rank = lower bound of the element's key among the sorted keys, searched directly in
+                    // SKEWED addresses a(q) = q + (q >> 5) so that no step pays for the skew: while the
+                    // steps are multiples of 32, pos is one too and a(pos + step - 1) = a(pos) + step +
+                    // step/32 - 2; the last five steps stay inside one 32-block, where a() is linear.
+                    // Slots [n, cap) hold the padding key 0xffffffff (never < key), so only the big
+                    // steps can leave the stored range [0, cap) and need a bound test; a big step is
+                    // never taken onto cap itself (slot cap-1 holds the padding or the largest key).
+                    // Addresses are 32-bit shared-memory BYTE addresses (one LDS with an immediate offset
+                    // per probe instead of index arithmetic + scaling).
+                    uint32_t rank[NPER];          // byte address of the element's (skewed) sorted slot
+                    const uint32_t so_b = smem_addr_u32(so);
+                    const uint32_t acap_b = so_b + 4u * (uint32_t)(cap + (cap >> 5));
 #pragma unroll
                     for (int r = 0; r < NPER; ++r) {
                         const int e = r * 32 + lane;
-                        uint32_t pos = 0;
+                        uint32_t ap = so_b;
                         if (e < n) {
                             const uint32_t key = score_key(e);
 #pragma unroll
-                            for (int step = 16 * NPER; step > 0; step >>= 1) {
-                                const uint32_t q = pos + step - 1;
-                                if (q < (uint32_t)n && so[q + (q >> 5)] < key) pos += step;
+                            for (int step = 16 * NPER; step >= 32; step >>= 1) {
+                                const uint32_t a = ap + 4u * (uint32_t)(step + (step >> 5) - 2);
+                                if (a < acap_b && lds_u32(a) < key) ap += 4u * (uint32_t)(step + (step >> 5));
                             }
+#pragma unroll
+                            for (int step = (NPER > 1 ? 16 : 16 * NPER); step > 0; step >>= 1)
+                                if (lds_u32(ap + 4u * (uint32_t)(step - 1)) < key) ap += 4u * (uint32_t)step;
                         }
-                        rank[r] = pos;
+                        rank[r] = ap;
                     }
                     __syncwarp();
 #pragma unroll
                     for (int r = 0; r < NPER; ++r) {
                         const int e = r * 32 + lane;
-                        if (e < n) so[rank[r] + (rank[r] >> 5)] = (uint32_t)e;
+                        if (e < n) sts_u32(rank[r], (uint32_t)e);
                     }
                     ordered = true;
                 }
@@ -328,30 +343,49 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 3 : 1)) nms_frames_
             // -- greedy walk, 32 candidates per step: every lane tests its own candidate against the
             // removed set, a ballot gives the alive ones; the lowest alive lane is by construction
             // the next kept box, its mask row is OR-ed in and kills later lanes of the same group.
+            // The inner loop is the kernel's hottest code (one trip per kept box): everything that does
+            // not depend on the kept box is hoisted -- the lane's column of the mask (mrow), the
+            // word / bit of the lane's own candidate (isrc, ibit) -- and the exact ZeroDivisionError
+            // test lives in a separate copy of the loop that only frames with a zero-union pair take.
             uint32_t rem = 0;        // lane w: word w of the removed set
             int cnt = 0;
             const int64_t blk = p.frame_major ? ((int64_t)off * C + (int64_t)c * n) : ((int64_t)c * p.n_rows + off);
             int32_t* out_idx = p.keep_idx + blk;
             uint8_t* out_m = p.keep_mask ? p.keep_mask + blk : nullptr;
             const unsigned lt = lanemask_lt();
+            const uint32_t mrow = smem_addr_u32(smask + (lane < Wn ? lane : 0));   // lanes beyond the row read word 0 ...
+            const uint32_t lmask = lane < Wn ? 0xffffffffu : 0u;                   // ... and drop it
+            const uint32_t row_bytes = (uint32_t)WS * 4u;
 #pragma unroll 1
             for (int g = 0; g < Wn; ++g) {
                 const bool valid = (g * 32 + lane) < n;
                 const uint32_t i = valid ? so[g * 33 + lane] : 0u;
-                const uint32_t w = __shfl_sync(FULL, rem, (int)(i >> 5));
-                unsigned alive = __ballot_sync(FULL, valid && !((w >> (i & 31)) & 1u));
+                const int isrc = (int)(i >> 5);
+                const uint32_t ibit = 1u << (i & 31);
+                const uint32_t w = __shfl_sync(FULL, rem, isrc);
+                unsigned alive = __ballot_sync(FULL, valid && !(w & ibit));
                 unsigned kgrp = 0;   // lanes of this group whose candidate is kept (warp-uniform)
-                while (alive) {
-                    const int l = __ffs(alive) - 1;
-                    const uint32_t ci = __shfl_sync(FULL, i, l);              // the kept box
-                    if (check_zero)
+                if (!check_zero) {
+                    while (alive) {
+                        const unsigned below = alive - 1u;                        // lowest alive lane = next kept box
+                        const uint32_t ci = __shfl_sync(FULL, i, __ffs(alive) - 1);
+                        const uint32_t roww = lds_u32(mrow + ci * row_bytes) & lmask;
+                        rem |= roww;
+                        kgrp |= alive & ~below;
+                        const uint32_t wv = __shfl_sync(FULL, roww, isrc);
+                        alive = alive & below & ~__ballot_sync(FULL, (wv & ibit) != 0u);
+                    }
+                } else {
+                    while (alive) {
+                        const int l = __ffs(alive) - 1;
+                        const uint32_t ci = __shfl_sync(FULL, i, l);
                         zero_division_check(so, Wn, sbox, sarea, rem, ci, g * 32 + l, n, lane, p.status);
-                    const uint32_t roww = (lane < Wn) ? smask[ci * WS + lane] : 0u;
-                    rem |= roww;
-                    kgrp |= (1u << l);
-                    const uint32_t wv = __shfl_sync(FULL, roww, (int)(i >> 5));
-                    alive &= ~__ballot_sync(FULL, (wv >> (i & 31)) & 1u);
-                    alive &= ~(1u << l);
+                        const uint32_t roww = lds_u32(mrow + ci * row_bytes) & lmask;
+                        rem |= roww;
+                        kgrp |= (1u << l);
+                        const uint32_t wv = __shfl_sync(FULL, roww, isrc);
+                        alive &= ~(__ballot_sync(FULL, (wv & ibit) != 0u) | (1u << l));
+                    }
                 }
                 // outputs of this group: kept rows in walk (= descending score) order, byte mask
                 const bool mine = (kgrp >> lane) & 1u;
@@ -398,16 +432,22 @@ static size_t nms_smem_bytes(int nb, int nper, int n_classes, bool stage) {
     return b;
 }
 
-template <int NPER>
-static int launch_nms_frames(const NmsFramesParams& p, size_t smem, int grid, cudaStream_t st) {
-    if (smem > max_dynamic_smem(nms_frames_kernel<NPER>)) {
+template <int NPER, bool STAGE>
+static int launch_nms_frames_t(const NmsFramesParams& p, size_t smem, int grid, cudaStream_t st) {
+    if (smem > max_dynamic_smem(nms_frames_kernel<NPER, STAGE>)) {
         set_error("nms_frames: %zu bytes of shared memory needed", smem);
         return VDET_ERR_UNSUPPORTED;
     }
-    VDET_CUDA(allow_dynamic_smem(nms_frames_kernel<NPER>, smem));
-    nms_frames_kernel<NPER><<<grid, NMS_THREADS, smem, st>>>(p);
+    VDET_CUDA(allow_dynamic_smem(nms_frames_kernel<NPER, STAGE>, smem));
+    nms_frames_kernel<NPER, STAGE><<<grid, NMS_THREADS, smem, st>>>(p);
     VDET_LAUNCH_CHECK();
     return VDET_OK;
+}
+
+template <int NPER>
+static int launch_nms_frames(const NmsFramesParams& p, size_t smem, int grid, cudaStream_t st) {
+    return p.stage ? launch_nms_frames_t<NPER, true>(p, smem, grid, st)
+                   : launch_nms_frames_t<NPER, false>(p, smem, grid, st);
 }
 
 
