@@ -15,6 +15,8 @@
 //      once: candidate i is kept iff its bit in the warp's `removed` set is clear, and a
 //      kept candidate ORs its mask row into the set (one word per lane).
 // The result is exactly the keep list of nms.pyx:43-66 for every (frame, class).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "warp_sort.cuh"
 
@@ -39,6 +41,7 @@ struct NmsFramesParams {
     int npad;          // big-frame variant: power-of-two sort length >= nb
     int fast_filter;   // 1: division-free threshold filter allowed (2^-20 <= T <= 2)
     float thresh_hi, thresh_lo;   // T(1 +- 2^-21) for that filter
+    int cls_chunk;     // classes staged in shared memory at a time (>= n_classes: all at once)
     int so_words;      // per-warp order scratch: (nb/32)*33 words
     int frame_major;   // output layout (VDET_LAYOUT_*)
     // work items: frames [0, split_from) are one item each; every later frame is cut into `nsplit`
@@ -148,7 +151,7 @@ __device__ __noinline__ void zero_division_check(const uint32_t* so, int ngroups
 // STAGE: the frame's scores are transposed into shared memory (as sort keys) in phase A; a
 // compile-time switch, so the per-element key fetch carries no trace of the other path.
 template <int NPER, bool STAGE>
-__global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 3 : 1)) nms_frames_kernel(const NmsFramesParams p) {
+__global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 4 : 1)) nms_frames_kernel(const NmsFramesParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NB = p.nb;
     const int W = NB >> 5;          // mask words per row (<= 32 in this variant)
@@ -199,26 +202,31 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 3 : 1)) nms_frames_
             all_sane &= box_sane(b);
         }
         const bool sane = __syncthreads_and(all_sane) != 0;     // CTA-uniform: cheaper pair test
-        if (STAGE) {
-            if (p.row_ids == nullptr && p.score_ldc == 1 && p.score_ldr == C) {
-                // contiguous [n, C] block: flat coalesced read, transposed conflict-free write
-                const float* src = p.scores + (int64_t)off * C;
-                const int total = n * C;
-                int r = tid / C, c = tid - r * C;                  // one division, then incremental
-                const int dr = NMS_THREADS / C, dc = NMS_THREADS - dr * C;
+        // Scores of classes [c0, c1) -> shared memory as sort keys, class-major (sscore[(c - c0) * SST + r]).
+        // The whole item is staged at once when it fits (cls_chunk >= classes of the item); otherwise
+        // in chunks, which lets four CTAs share an SM instead of three.
+        auto stage_scores = [&](const int c0, const int c1) {
+            const int CH = c1 - c0;
+            const int total = n * CH;
+            if (p.row_ids == nullptr && p.score_ldc == 1) {
+                // contiguous rows: coalesced reads along the class axis, transposed conflict-free writes
+                const float* src = p.scores + (int64_t)off * p.score_ldr + c0;
+                int r = tid / CH, c = tid - r * CH;                // one division, then incremental
+                const int dr = NMS_THREADS / CH, dc = NMS_THREADS - dr * CH;
                 for (int f = tid; f < total; f += NMS_THREADS) {
-                    sscore[c * SST + r] = f32_key_desc(__ldg(src + f));
+                    sscore[c * SST + r] = f32_key_desc(__ldg(src + (int64_t)r * p.score_ldr + c));
                     r += dr; c += dc;
-                    if (c >= C) { c -= C; ++r; }
+                    if (c >= CH) { c -= CH; ++r; }
                 }
             } else {
-                const int total = n * C;
                 for (int f = tid; f < total; f += NMS_THREADS) {
-                    const int r = f / C, c = f - r * C;
-                    sscore[c * SST + r] = f32_key_desc(__ldg(p.scores + (int64_t)srow[r] * p.score_ldr + (int64_t)c * p.score_ldc));
+                    const int r = f / CH, c = f - r * CH;
+                    sscore[c * SST + r] = f32_key_desc(__ldg(p.scores + (int64_t)srow[r] * p.score_ldr + (int64_t)(c0 + c) * p.score_ldc));
                 }
             }
-        }
+        };
+        const int chunk = STAGE ? p.cls_chunk : (c_end - c_begin);
+        if (STAGE) stage_scores(c_begin, min(c_begin + chunk, c_end));
         // ---- B: suppression bit matrix, original index space, upper-triangular tiles -------
         {
             const int Wn = (n + 31) >> 5;          // blocks actually populated by this frame
@@ -253,8 +261,15 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 3 : 1)) nms_frames_
         // ---- C: per class: order by score + greedy walk (one warp per class) ---------------
         uint32_t* so = sord + warp * p.so_words;          // this warp's order scratch (skewed)
         const int cap = Wn * 32;                          // sorted positions >= cap are padding
-        for (int c = c_begin + warp; c < c_end; c += NMS_WARPS) {
-            const uint32_t* sc_smem = sscore + c * SST;
+        for (int c0 = c_begin; c0 < c_end; c0 += chunk) {
+        const int c1 = min(c0 + chunk, c_end);
+        if (STAGE && c0 != c_begin) {
+            __syncthreads();                              // every warp is done with the previous chunk's keys
+            stage_scores(c0, c1);
+            __syncthreads();
+        }
+        for (int c = c0 + warp; c < c1; c += NMS_WARPS) {
+            const uint32_t* sc_smem = sscore + (c - c0) * SST;
             const float* sc_glob = p.scores + (int64_t)c * p.score_ldc;
             auto score_key = [&](const int e) -> uint32_t {
                 return STAGE ? sc_smem[e] : f32_key_desc(__ldg(sc_glob + (int64_t)srow[e] * p.score_ldr));
@@ -401,6 +416,7 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 3 : 1)) nms_frames_
             if (lane == 0) p.keep_cnt[p.frame_major ? ((int64_t)seg * C + c) : ((int64_t)c * p.n_segs + seg)] = cnt;
             __syncwarp();
         }
+        }                  // class chunks
         __syncthreads();   // smem is reused by the next frame
     }
 }
@@ -782,7 +798,7 @@ extern "C" int vdet_nms_frames_f32(const float* boxes, int box_ld,
         return VDET_ERR_UNSUPPORTED;
     }
     NmsFramesParams p;
-    p.gmask = nullptr; p.npad = 0;
+    p.gmask = nullptr; p.npad = 0; p.cls_chunk = n_classes;
     p.frame_major = (out_layout == VDET_LAYOUT_FRAME_MAJOR) ? 1 : 0;
     {
         const float Tf = thresh_ceil_f32(thresh);
@@ -827,15 +843,44 @@ extern "C" int vdet_nms_frames_f32(const float* boxes, int box_ld,
     p.so_words = (nb / 32) * 33;
     int nper = 1;                                                           // sort network: 32*nper >= nb
     while (32 * nper < nb) nper <<= 1;
-    // Stage scores when the block is box-major and the CTA still fits >= 2 per SM.
+    // Stage scores when the block is box-major and the CTA still fits >= 2 per SM.  Residency: the
+    // register budget allows 4 CTAs per SM (64 registers x 256 threads; 1 for the 1024-box variant);
+    // shared memory decides the rest.  When staging every class at once would cost a CTA slot, the
+    // classes are staged in up to 3 chunks (multiples of the warp count) instead.
     const bool want_stage = (score_ldr != 1);
-    const size_t smem_stage = nms_smem_bytes(nb, nper, n_classes, true);
-    p.stage = (want_stage && smem_stage <= 100 * 1024) ? 1 : 0;
-    const size_t smem = nms_smem_bytes(nb, nper, n_classes, p.stage != 0);
-    int per_sm = (int)((size_t)(220 * 1024) / (smem + 1024));
+    const size_t base = nms_smem_bytes(nb, nper, 0, false);
+    const size_t per_class = (size_t)(nb + 1) * sizeof(float);
+    const size_t sm_smem = 228 * 1024, cta_reserved = 1024;
+    const int reg_limit = (nper > 16) ? 1 : 4;
+    auto fit = [&](size_t smem_cta) {                       // CTAs of that size per SM
+        int k = (int)(sm_smem / (smem_cta + cta_reserved));
+        return k > reg_limit ? reg_limit : k;
+    };
+    p.stage = (want_stage && base + n_classes * per_class <= 100 * 1024) ? 1 : 0;
+    p.cls_chunk = n_classes;
+    int per_sm = fit(base + (p.stage ? n_classes * per_class : 0));
+    int forced = 0;
+    if (const char* e = getenv("VDET_NMS_PER_SM")) forced = atoi(e);      // measurement hook
+    if (p.stage && n_classes > NMS_WARPS) {
+        for (int want = reg_limit; want > per_sm; --want) {
+            if (forced > 0 && want > forced) continue;
+            const size_t budget = sm_smem / want - cta_reserved;
+            if (budget <= base) continue;
+            const int chunk_max = (int)((budget - base) / per_class);
+            if (chunk_max < NMS_WARPS) continue;
+            const int n_pass = (n_classes + chunk_max - 1) / chunk_max;
+            if (n_pass > 3) continue;
+            int chunk = (n_classes + n_pass - 1) / n_pass;
+            const int rounded = (chunk + NMS_WARPS - 1) / NMS_WARPS * NMS_WARPS;
+            if (rounded <= chunk_max) chunk = rounded;
+            p.cls_chunk = chunk;
+            per_sm = want;
+            break;
+        }
+    }
+    if (forced > 0 && per_sm > forced) per_sm = forced;
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 8) per_sm = 8;
-    if (nper > 16) per_sm = 1; else if (per_sm > 3) per_sm = 3;      // register-limited residency
+    const size_t smem = base + (p.stage ? (size_t)(p.cls_chunk < n_classes ? p.cls_chunk : n_classes) * per_class : 0);
     int grid = usable_sm_count() * per_sm;
     plan_items(p, grid);
     if (grid > p.n_items) grid = p.n_items;
