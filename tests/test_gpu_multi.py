@@ -62,6 +62,19 @@ def _worker(rank, world, port, T, N, C, thr, out_dir):
     pp = ShardedVideoPostProcessor(e - a, N, C, thr, dev)
     pp.pp.stage(b[a:e], s[a:e])
     res = pp.step_host()
+    # the device-resident step (what bench.py's `value` times) on the same shard: local link first,
+    # boundary link last -- must give the same arrays as the staged step
+    dev_res = pp.step_device(pp.pp.d_boxes, pp.pp.d_scores)
+    torch.cuda.synchronize()
+    for key in ("keep_mask", "keep_cnt", "succ", "link_iou"):
+        assert np.array_equal(dev_res[key].cpu().numpy().reshape(np.asarray(res[key]).shape), np.asarray(res[key])), key
+    # two steps in flight through the boundary exchange
+    t0 = pp.submit_host()
+    t1 = pp.submit_host()
+    r0 = {k: np.array(v, copy=True) for k, v in pp.collect(t0).items()}
+    r1 = pp.collect(t1)
+    for key in ("keep_mask", "keep_cnt", "succ", "link_iou"):
+        assert np.array_equal(r0[key], np.asarray(res[key])) and np.array_equal(np.asarray(r1[key]), np.asarray(res[key])), key
     # frame-sharded vid_nms of one class with the global keep-order merge
     from vdetlib_b200.dist import sharded_vid_nms
     s_glob = s[:, :, 0] + np.arange(T)[:, None] * 1e-5                      # unique across the video

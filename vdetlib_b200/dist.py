@@ -70,6 +70,7 @@ class ShardedVideoPostProcessor(object):
         self.exchange = BoundaryExchange(n_boxes, self.pp.device, group)
         self.side = torch.cuda.Stream(device=self.pp.device, priority=-1)
         self.n_boxes = n_boxes
+        self._seg_last = torch.tensor([0, int(n_boxes)], dtype=torch.int32, device=self.pp.device)
         if self.exchange.world > 1:
             from . import _lib
             _lib.load().vdet_set_reserved_sms(2)       # room for the all-gather next to the NMS grid
@@ -87,19 +88,27 @@ class ShardedVideoPostProcessor(object):
         """Device-resident inputs; returns the result dict of VideoPostProcessor.run_device.
         On a single rank there is no exchange and the step is replayed from a CUDA graph.
 
-        The boundary all-gather is enqueued first, on a side stream, and overlaps the NMS kernel: with
-        more than one rank a few SMs are kept out of the persistent NMS grid (vdet_set_reserved_sms)
-        so that the NCCL kernel is scheduled immediately; the link kernel then waits on it."""
+        The boundary all-gather is enqueued first, on a side stream, and overlaps the link of the
+        shard's own frames; with more than one rank a few SMs are also kept out of the persistent NMS
+        grid (vdet_set_reserved_sms) so that a collective still waiting for a slow peer does not hold
+        back an NMS CTA.  Only the last frame's link (one small launch at the end) needs the halo."""
         from . import ops
         pp = self.pp
         if self.exchange.world == 1:
             return pp.run_device(d_boxes, d_scores, None, graph=True)
         main = torch.cuda.current_stream()
-        halo = self._exchange(d_boxes[:self.n_boxes])
-        out = ops.nms_frames(d_boxes, d_scores, pp.seg_offsets, pp.nms_thresh, pp.N, want_mask=True,
+        N, T = self.n_boxes, pp.T
+        halo = self._exchange(d_boxes[:N])
+        # every frame but the last links inside the shard: that launch needs no halo and runs first,
+        # with the all-gather beside it (its short-lived CTAs leave room for the NCCL kernel at once;
+        # behind the persistent NMS grid the collective would only start when the first CTAs retire)
+        succ, link_iou = ops.link_frames(d_boxes, pp.seg_offsets, N, None, out=(pp.d_succ, pp.d_iou))
+        out = ops.nms_frames(d_boxes, d_scores, pp.seg_offsets, pp.nms_thresh, N, want_mask=True,
                              status=pp.status, frame_major_out=True, out=(pp.d_idx, pp.d_cnt, pp.d_mask))
         main.wait_stream(self.side)
-        succ, link_iou = ops.link_frames(d_boxes, pp.seg_offsets, pp.N, halo, out=(pp.d_succ, pp.d_iou))
+        if halo is not None:                       # the last frame against the neighbour's first frame
+            lo = (T - 1) * N
+            ops.link_frames(d_boxes[lo:], self._seg_last, N, halo, out=(succ[lo:], link_iou[lo:]))
         res = pp._views(out)
         res.update(succ=succ, link_iou=link_iou)
         return res
