@@ -71,6 +71,7 @@ class ShardedVideoPostProcessor(object):
         self.side = torch.cuda.Stream(device=self.pp.device, priority=-1)
         self.n_boxes = n_boxes
         self._seg_last = torch.tensor([0, int(n_boxes)], dtype=torch.int32, device=self.pp.device)
+        self._graphs, self._graph_res, self._graph_refused = {}, None, False
         if self.exchange.world > 1:
             from . import _lib
             _lib.load().vdet_set_reserved_sms(2)       # room for the all-gather next to the NMS grid
@@ -84,18 +85,47 @@ class ShardedVideoPostProcessor(object):
             halo = self.exchange.finish(handle, count_hint=self.n_boxes)
         return halo
 
-    def step_device(self, d_boxes, d_scores):
+    def step_device(self, d_boxes, d_scores, graph=True):
         """Device-resident inputs; returns the result dict of VideoPostProcessor.run_device.
-        On a single rank there is no exchange and the step is replayed from a CUDA graph.
+        The step is replayed from a CUDA graph captured on first use for this pair of input buffers
+        (``graph=False``: plain stream launches).  With more than one rank the graph contains the
+        boundary all-gather as well: enqueuing a NCCL collective from Python costs more host time than
+        the kernels of this step take on the device.  If the capture is refused the step stays eager.
 
         The boundary all-gather is enqueued first, on a side stream, and overlaps the link of the
         shard's own frames; with more than one rank a few SMs are also kept out of the persistent NMS
         grid (vdet_set_reserved_sms) so that a collective still waiting for a slow peer does not hold
         back an NMS CTA.  Only the last frame's link (one small launch at the end) needs the halo."""
-        from . import ops
         pp = self.pp
         if self.exchange.world == 1:
-            return pp.run_device(d_boxes, d_scores, None, graph=True)
+            return pp.run_device(d_boxes, d_scores, None, graph=graph)
+        if not graph or self._graph_refused:
+            return self._step_device_eager(d_boxes, d_scores)
+        key = (d_boxes.data_ptr(), d_scores.data_ptr())
+        g = self._graphs.get(key)
+        if g is None:
+            res = self._step_device_eager(d_boxes, d_scores)        # warm-up outside the capture
+            torch.cuda.synchronize(self.pp.device)
+            try:
+                g = torch.cuda.CUDAGraph()
+                # thread_local: the NCCL watchdog thread polls events while this thread captures
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    res = self._step_device_eager(d_boxes, d_scores)
+            except Exception as e:                                    # noqa: BLE001 -- stay eager, say so once
+                import sys
+                sys.stderr.write("vdetlib_b200.dist: CUDA-graph capture of the sharded step refused (%r); "
+                                 "running eagerly\n" % (e,))
+                self._graph_refused = True
+                torch.cuda.synchronize(self.pp.device)
+                return self._step_device_eager(d_boxes, d_scores)
+            self._graphs[key] = g
+            self._graph_res = res
+        g.replay()
+        return self._graph_res
+
+    def _step_device_eager(self, d_boxes, d_scores):
+        from . import ops
+        pp = self.pp
         main = torch.cuda.current_stream()
         N, T = self.n_boxes, pp.T
         halo = self._exchange(d_boxes[:N])
