@@ -34,8 +34,9 @@ class BoundaryExchange(object):
         self.send = torch.zeros((self.max_boxes + 1, 4), dtype=torch.float32, device=self.device)
         self.recv = torch.zeros((self.world, self.max_boxes + 1, 4), dtype=torch.float32, device=self.device)
 
-    def start(self, first_frame_boxes):
-        """Enqueue the all-gather (async when the backend supports it); returns a handle."""
+    def start(self, first_frame_boxes, async_op=True):
+        """Enqueue the all-gather; returns a handle (None for ``async_op=False``: the collective is then
+        ordered on the current stream, which is also the form a CUDA-graph capture accepts)."""
         n = int(first_frame_boxes.shape[0])
         if n > self.max_boxes:
             raise ValueError("first frame has %d boxes > max_boxes %d" % (n, self.max_boxes))
@@ -43,18 +44,17 @@ class BoundaryExchange(object):
         self.send[self.max_boxes, 0] = float(n)
         if self.world == 1:
             return None
-        return dist.all_gather_into_tensor(self.recv.view(-1, 4), self.send, group=self.group, async_op=True)
+        return dist.all_gather_into_tensor(self.recv.view(-1, 4), self.send, group=self.group, async_op=async_op)
 
     def finish(self, handle, count_hint=None):
         """Wait and return the halo = boxes of the next rank's first frame (None on the last rank).
 
         ``count_hint``: the neighbour's box count when it is known a priori (uniform frames);
         avoids reading the count back from the device."""
+        if handle is not None:
+            handle.wait()
         if self.world == 1 or self.rank == self.world - 1:
-            if handle is not None:
-                handle.wait()
             return None
-        handle.wait()
         slot = self.recv[self.rank + 1]
         n = int(count_hint) if count_hint is not None else int(slot[self.max_boxes, 0].item())
         return slot[:n]
@@ -81,7 +81,8 @@ class ShardedVideoPostProcessor(object):
         main = torch.cuda.current_stream()
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
-            handle = self.exchange.start(d_first_frame)
+            # stream-ordered on the side stream (no internal NCCL stream to join: capturable)
+            handle = self.exchange.start(d_first_frame, async_op=False)
             halo = self.exchange.finish(handle, count_hint=self.n_boxes)
         return halo
 
