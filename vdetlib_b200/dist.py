@@ -34,9 +34,8 @@ class BoundaryExchange(object):
         self.send = torch.zeros((self.max_boxes + 1, 4), dtype=torch.float32, device=self.device)
         self.recv = torch.zeros((self.world, self.max_boxes + 1, 4), dtype=torch.float32, device=self.device)
 
-    def start(self, first_frame_boxes, async_op=True):
-        """Enqueue the all-gather; returns a handle (None for ``async_op=False``: the collective is then
-        ordered on the current stream, which is also the form a CUDA-graph capture accepts)."""
+    def start(self, first_frame_boxes):
+        """Enqueue the all-gather (async when the backend supports it); returns a handle."""
         n = int(first_frame_boxes.shape[0])
         if n > self.max_boxes:
             raise ValueError("first frame has %d boxes > max_boxes %d" % (n, self.max_boxes))
@@ -44,17 +43,18 @@ class BoundaryExchange(object):
         self.send[self.max_boxes, 0] = float(n)
         if self.world == 1:
             return None
-        return dist.all_gather_into_tensor(self.recv.view(-1, 4), self.send, group=self.group, async_op=async_op)
+        return dist.all_gather_into_tensor(self.recv.view(-1, 4), self.send, group=self.group, async_op=True)
 
     def finish(self, handle, count_hint=None):
         """Wait and return the halo = boxes of the next rank's first frame (None on the last rank).
 
         ``count_hint``: the neighbour's box count when it is known a priori (uniform frames);
         avoids reading the count back from the device."""
-        if handle is not None:
-            handle.wait()
         if self.world == 1 or self.rank == self.world - 1:
+            if handle is not None:
+                handle.wait()
             return None
+        handle.wait()
         slot = self.recv[self.rank + 1]
         n = int(count_hint) if count_hint is not None else int(slot[self.max_boxes, 0].item())
         return slot[:n]
@@ -70,8 +70,6 @@ class ShardedVideoPostProcessor(object):
         self.exchange = BoundaryExchange(n_boxes, self.pp.device, group)
         self.side = torch.cuda.Stream(device=self.pp.device, priority=-1)
         self.n_boxes = n_boxes
-        self._seg_last = torch.tensor([0, int(n_boxes)], dtype=torch.int32, device=self.pp.device)
-        self._graphs, self._graph_res, self._graph_refused = {}, None, False
         if self.exchange.world > 1:
             from . import _lib
             _lib.load().vdet_set_reserved_sms(2)       # room for the all-gather next to the NMS grid
@@ -81,65 +79,32 @@ class ShardedVideoPostProcessor(object):
         main = torch.cuda.current_stream()
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
-            # stream-ordered on the side stream (no internal NCCL stream to join: capturable)
-            handle = self.exchange.start(d_first_frame, async_op=False)
+            handle = self.exchange.start(d_first_frame)
             halo = self.exchange.finish(handle, count_hint=self.n_boxes)
         return halo
 
-    def step_device(self, d_boxes, d_scores, graph=True):
+    def step_device(self, d_boxes, d_scores):
         """Device-resident inputs; returns the result dict of VideoPostProcessor.run_device.
-        The step is replayed from a CUDA graph captured on first use for this pair of input buffers
-        (``graph=False``: plain stream launches).  With more than one rank the graph contains the
-        boundary all-gather as well: enqueuing a NCCL collective from Python costs more host time than
-        the kernels of this step take on the device.  If the capture is refused the step stays eager.
+        On a single rank there is no exchange and the step is replayed from a CUDA graph.
 
-        The boundary all-gather is enqueued first, on a side stream, and overlaps the link of the
-        shard's own frames; with more than one rank a few SMs are also kept out of the persistent NMS
-        grid (vdet_set_reserved_sms) so that a collective still waiting for a slow peer does not hold
-        back an NMS CTA.  Only the last frame's link (one small launch at the end) needs the halo."""
-        pp = self.pp
-        if self.exchange.world == 1:
-            return pp.run_device(d_boxes, d_scores, None, graph=graph)
-        if not graph or self._graph_refused:
-            return self._step_device_eager(d_boxes, d_scores)
-        key = (d_boxes.data_ptr(), d_scores.data_ptr())
-        g = self._graphs.get(key)
-        if g is None:
-            res = self._step_device_eager(d_boxes, d_scores)        # warm-up outside the capture
-            torch.cuda.synchronize(self.pp.device)
-            try:
-                g = torch.cuda.CUDAGraph()
-                # thread_local: the NCCL watchdog thread polls events while this thread captures
-                with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                    res = self._step_device_eager(d_boxes, d_scores)
-            except Exception as e:                                    # noqa: BLE001 -- stay eager, say so once
-                import sys
-                sys.stderr.write("vdetlib_b200.dist: CUDA-graph capture of the sharded step refused (%r); "
-                                 "running eagerly\n" % (e,))
-                self._graph_refused = True
-                torch.cuda.synchronize(self.pp.device)
-                return self._step_device_eager(d_boxes, d_scores)
-            self._graphs[key] = g
-            self._graph_res = res
-        g.replay()
-        return self._graph_res
+        The boundary all-gather is enqueued first, on a side stream, and overlaps the NMS kernel: with
+        more than one rank a few SMs are kept out of the persistent NMS grid (vdet_set_reserved_sms)
+        so that the NCCL kernel is scheduled immediately; the link kernel then waits on it.
 
-    def _step_device_eager(self, d_boxes, d_scores):
+        Measured alternatives that did not pay (2 x B200, profiles/r01_scaling.md): linking the
+        shard's own frames first and only the last frame after the exchange (0.55-0.56 ms/step
+        against 0.54), and replaying the sharded step from a CUDA graph -- torch refuses the capture
+        of this fork/join around the NCCL all-gather ("capturing stream has unjoined work")."""
         from . import ops
         pp = self.pp
+        if self.exchange.world == 1:
+            return pp.run_device(d_boxes, d_scores, None, graph=True)
         main = torch.cuda.current_stream()
-        N, T = self.n_boxes, pp.T
-        halo = self._exchange(d_boxes[:N])
-        # every frame but the last links inside the shard: that launch needs no halo and runs first,
-        # with the all-gather beside it (its short-lived CTAs leave room for the NCCL kernel at once;
-        # behind the persistent NMS grid the collective would only start when the first CTAs retire)
-        succ, link_iou = ops.link_frames(d_boxes, pp.seg_offsets, N, None, out=(pp.d_succ, pp.d_iou))
-        out = ops.nms_frames(d_boxes, d_scores, pp.seg_offsets, pp.nms_thresh, N, want_mask=True,
+        halo = self._exchange(d_boxes[:self.n_boxes])
+        out = ops.nms_frames(d_boxes, d_scores, pp.seg_offsets, pp.nms_thresh, pp.N, want_mask=True,
                              status=pp.status, frame_major_out=True, out=(pp.d_idx, pp.d_cnt, pp.d_mask))
         main.wait_stream(self.side)
-        if halo is not None:                       # the last frame against the neighbour's first frame
-            lo = (T - 1) * N
-            ops.link_frames(d_boxes[lo:], self._seg_last, N, halo, out=(succ[lo:], link_iou[lo:]))
+        succ, link_iou = ops.link_frames(d_boxes, pp.seg_offsets, pp.N, halo, out=(pp.d_succ, pp.d_iou))
         res = pp._views(out)
         res.update(succ=succ, link_iou=link_iou)
         return res
