@@ -1,5 +1,5 @@
 #!/bin/bash
-# Multi-GPU verification only (no single-GPU suite): parity test on all GPUs + bench at N = 2,4,8.
+# Multi-GPU verification only (no single-GPU suite): parity test on all GPUs + bench at N = 2,4,8 + host/device probe.
 set -u
 mkdir -p gpurun_out
 cd "${GRAFT_REPO_ROOT:-.}"
@@ -14,5 +14,8 @@ for n in 2 4 8; do
     timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29518 \
         bench.py --gpus $n --steps 50 --warmup 5 > gpurun_out/bench_n$n.json 2> gpurun_out/bench_n$n.err
     echo "bench n=$n rc=$?"; cat gpurun_out/bench_n$n.json | cut -c1-400; tail -n 3 gpurun_out/bench_n$n.err
+    timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29519 \
+        tools/multi_probe.py > gpurun_out/multi_probe_n$n.json 2> gpurun_out/multi_probe_n$n.err
+    echo "probe n=$n rc=$?"; cat gpurun_out/multi_probe_n$n.json | tr -d '\n'; echo
   fi
 done
