@@ -285,7 +285,9 @@ def run_b200(args):
     traffic = None            # dram read+write of that kernel from the committed ncu --set full capture
     warp_inst = None          # and its executed warp instructions (same capture), for the issue roofline
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu.json")))["kernels"]
+        import glob
+        ncu_json = sorted(glob.glob(os.path.join(ROOT, "profiles", "r[0-9]*_ncu.json")))[-1]     # newest round
+        prof = json.load(open(ncu_json))["kernels"]
         for name, caps in prof.items():
             if dom in name and caps[0].get("dram_read") is not None:
                 scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -312,7 +314,8 @@ def run_b200(args):
                              "achieved_warp_inst_per_s": warp_inst / (dom_ms / 1000.0),
                              "peak_warp_inst_per_s": issue_peak, "frac": warp_inst / (dom_ms / 1000.0) / issue_peak,
                              "sm_count": props.multi_processor_count, "sm_clock_hz": sm_hz,
-                             "source": "profiles/r01_ncu.json (ncu --set full of this kernel) / live CUDA-event time"}
+                             "source": "profiles/%s (ncu --set full of this kernel) / live CUDA-event time"
+                                       % os.path.basename(ncu_json)}
 
     # ---- the IoU-matrix kernel against HBM (BASELINE.json: "% HBM peak on IoU kernel") -----
     A = 16384
