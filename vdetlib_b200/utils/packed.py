@@ -503,3 +503,193 @@ def pack_det_dir(vid_proto, det_dir, out_path=None):
     if out_path is not None:
         dets.save(out_path)
     return dets
+
+
+# ------------------------------------------------------------------------------------------
+# the temporal kernels' view of a score proto
+# ------------------------------------------------------------------------------------------
+class PackedTubelets(object):
+    """A score proto (utils/protocol.py:111-154) as ragged arrays: ``offsets`` int64 [K+1] and one flat
+    column per numeric box field (``det_score``, ``frame``, ``anchor``, ``track_score`` ..., ``bbox`` as
+    [n,4]).  The temporal stages of vdet/tubelet_cls.py run on ``padded(key)`` = [K, Lmax] rows +
+    lengths -- exactly what the dict adapters build with a Python loop per call -- and write back with
+    ``set_padded``; ``to_score_proto()`` returns the dict form with the updated values.
+
+    In-place stages (same arithmetic, kernels and exceptions as the dict adapters of
+    vdetlib_b200.vdet.tubelet_cls): ``complete_scores_`` (:284-303), ``temporal_maxpool_`` (:386-414),
+    ``conv_scores_`` (:15-51 with a TemporalConvNet)."""
+
+    def __init__(self, meta, arrays):
+        if meta.get("kind") != "score":
+            raise ValueError("not a packed score proto")
+        self.meta = json.loads(json.dumps(meta))                  # private copy: stages edit it
+        self.arrays = dict(arrays)
+        self.offsets = np.asarray(arrays["tub.__offsets"], dtype=np.int64)
+
+    @classmethod
+    def from_score_proto(cls, score_proto):
+        meta, arrays = pack_proto(score_proto)
+        return cls(meta, arrays)
+
+    @classmethod
+    def load(cls, path, mmap=True):
+        return cls(*load_packed(path, mmap=mmap))
+
+    def save(self, path):
+        save_packed(path, self.meta, self.arrays)
+
+    def to_score_proto(self):
+        return unpack_proto(self.meta, self.arrays)
+
+    # ---- columns -----------------------------------------------------------------------------
+    @property
+    def n_tubelets(self):
+        return len(self.offsets) - 1
+
+    @property
+    def lengths(self):
+        return np.diff(self.offsets).astype(np.int32)
+
+    def _col(self, key):
+        col = self.meta["boxes"]["cols"].get(key)
+        if col is None or col["t"] not in ("num", "vec") or not col["all"]:
+            raise KeyError("score proto has no regular numeric box field %r" % key)
+        return col
+
+    def column(self, key):
+        """Flat float64 values of a box field, tubelet after tubelet (read-only view)."""
+        self._col(key)
+        return np.asarray(self.arrays["tub." + key])
+
+    def head(self, key):
+        """Per-tubelet values of a tubelet field (``class_index``, ``gt`` ...)."""
+        col = self.meta["tubelets"]["cols"][key]
+        return _column_values(col, "tubhead." + key, self.arrays)
+
+    def padded(self, key="det_score", fill=0.0):
+        """``(rows float64 [K', Lmax], lengths int32 [K'], index int64 [K'])`` over the tubelets that
+        have at least one box (what the dict adapters process); padding = ``fill``."""
+        vals = self.column(key).astype(np.float64, copy=False)
+        lens = self.lengths
+        index = np.nonzero(lens > 0)[0]
+        lens = lens[index]
+        L = int(lens.max()) if len(lens) else 0
+        rows = np.full((len(index), max(L, 1)), fill, dtype=np.float64)
+        if len(index):
+            col_id = np.arange(max(L, 1))[None, :]
+            take = col_id < lens[:, None]
+            rows[take] = vals                                       # row-major: tubelet after tubelet
+        return rows, lens, index
+
+    def set_padded(self, key, rows, lens, where=None):
+        """Scatter padded rows back into the flat column ``key`` (created if the proto has none, placed
+        last in every box -- ``conv_score``).  ``where`` (bool [K', Lmax]) restricts the update."""
+        rows = np.asarray(rows, dtype=np.float64)
+        take = np.arange(rows.shape[1])[None, :] < np.asarray(lens)[:, None]
+        name = "tub." + key
+        cols = self.meta["boxes"]["cols"]
+        if key not in cols:
+            if int(take.sum()) != int(self.offsets[-1]):
+                raise ValueError("a new box field must be written for every box")
+            cols[key] = {"all": True, "t": "num", "int": "none"}
+            for order in self.meta["boxes"]["orders"]:
+                order.append(key)
+            self.arrays[name] = rows[take].copy()
+            return
+        self._col(key)
+        flat = np.array(self.arrays[name], dtype=np.float64, copy=True)   # mmap / shared -> private
+        new = rows[take]
+        if where is None:
+            flat[...] = new
+            changed = np.ones(flat.shape, dtype=bool)
+        else:
+            changed = np.asarray(where, dtype=bool)[take]
+            flat[changed] = new[changed]
+        self.arrays[name] = flat
+        # the written values are floats: fix the int/float type map of the column
+        col = cols[key]
+        if col["int"] == "all":
+            ints = ~changed
+        elif col["int"] == "map":
+            ints = np.unpackbits(np.asarray(self.arrays[name + "__int"]), count=flat.size).astype(bool) & ~changed
+        else:
+            ints = None
+        if ints is not None:
+            self.arrays.pop(name + "__int", None)
+            if ints.all():
+                col["int"] = "all"
+            elif not ints.any():
+                col["int"] = "none"
+            else:
+                col["int"] = "map"
+                self.arrays[name + "__int"] = np.packbits(ints)
+
+    # ---- stages (GPU) ------------------------------------------------------------------------
+    @staticmethod
+    def _to_dev(a, device):
+        import torch
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    def complete_scores_(self, device=None):
+        """do_score_completion (vdet/tubelet_cls.py:284-303): runs of ``det_score <= -10`` are filled from
+        their valid neighbours; IndexError when a tubelet has no valid score at all (:295)."""
+        from .. import ops
+        rows, lens, _ = self.padded("det_score")
+        if not len(lens):
+            return self
+        missing = ~(rows > -10)                                     # before the kernel: rows may alias the tensor
+        dev_rows = self._to_dev(rows, device)
+        status = ops.score_completion_(dev_rows, self._to_dev(lens, device))
+        ops.raise_for_status(status)
+        self.set_padded("det_score", dev_rows.cpu().numpy(), lens, where=missing)
+        return self
+
+    def temporal_maxpool_(self, window_size, device=None):
+        """score_proto_temporal_maxpool (vdet/tubelet_cls.py:386-414).  ValueError for an even window or
+        a gt tubelet -- raised BEFORE anything is written (the reference has rewritten the tubelets in
+        front of the gt one by then, :395-412)."""
+        from .. import ops
+        if window_size == 1:
+            return self
+        if window_size % 2 != 1:
+            raise ValueError('Window size must be odd!')
+        if "gt" in self.meta["tubelets"]["cols"] and any(g == 1 for g in self.head("gt")):
+            raise ValueError('Dangerous: Score file contains gt tracks!')
+        self.meta["top"]["method"] = self.meta["top"]["method"] + '_temporal_maxpool_{}'.format(window_size)
+        rows, lens, _ = self.padded("det_score", fill=-1e5)
+        if len(lens):
+            out = ops.temporal_maxpool(self._to_dev(rows, device), window_size, self._to_dev(lens, device))
+            self.set_padded("det_score", out.cpu().numpy(), lens)
+        return self
+
+    def conv_scores_(self, net, device=None):
+        """score_conv_cls (vdet/tubelet_cls.py:15-51) with a TemporalConvNet: writes ``conv_score``."""
+        from .. import ops
+        lens_all = self.lengths
+        lens = lens_all[lens_all > 0]                               # empty tubelets have no box to score
+        if not len(lens):
+            return self
+        lens_dev = self._to_dev(lens, device)
+        total = None
+        length = np.repeat(lens.astype(np.float64), lens)           # tubelet length per box
+        for name, taps in net.taps.items():
+            if name == 'det_scores':
+                flat = self.column('det_score')
+            elif name == 'track_scores':
+                flat = self.column('track_score')
+            elif name == 'anchors':
+                flat = self.column('anchor') * 1. / length                          # :28
+            elif name == 'abs_anchors':
+                flat = np.abs(self.column('anchor') * 1. / length)                  # :30
+            elif name == 'gt_overlaps':
+                flat = self.column('gt_overlap')
+            else:
+                raise KeyError(name)
+            rows = np.zeros((len(lens), int(lens.max())), dtype=np.float64)
+            rows[np.arange(rows.shape[1])[None, :] < lens[:, None]] = flat
+            y = ops.temporal_conv1d(self._to_dev(rows, device), self._to_dev(np.asarray(taps, np.float64).reshape(1, -1), device),
+                                    net.pad_mode, lens_dev)
+            total = y if total is None else total + y
+        self.set_padded("conv_score", (total + net.bias).cpu().numpy(), lens)
+        return self
