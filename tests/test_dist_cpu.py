@@ -65,3 +65,71 @@ def test_boundary_exchange_gloo(tmp_path, world):
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert open(os.path.join(str(tmp_path), "rank%d" % r)).read() == "ok"
+
+
+def _temporal_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle_np
+    from vdetlib_b200.dist import ShardedTemporalRows, frame_sharded_window_op, shard_range
+    rng = np.random.default_rng(1)
+    rows = rng.uniform(-1, 1, (11, 53))                                  # every rank knows the whole block
+    ok = True
+    # by tubelet: local stage, then gather
+    sh = ShardedTemporalRows(rows.shape[0])
+    mine = np.stack([oracle_np.temporal_maxpool_row(r, 5) for r in sh.local(rows)]) if sh.stop > sh.start \
+        else np.zeros((0, rows.shape[1]))
+    full = sh.gather(torch.from_numpy(mine)).numpy()
+    want = np.stack([oracle_np.temporal_maxpool_row(r, 5) for r in rows])
+    ok = ok and np.array_equal(full, want)
+    # by frame: halo exchange, then the window op on the haloed block
+    a, b = shard_range(rows.shape[1], world, rank)
+    local = torch.from_numpy(rows[:, a:b].copy())
+    for w in (3, 9):
+        h = w // 2
+
+        def maxpool(ext):
+            return torch.from_numpy(np.stack([oracle_np.temporal_maxpool_row(r, w) for r in ext.numpy()]))
+        got = frame_sharded_window_op(local, h, maxpool, pad_value=-1e5).numpy()
+        want = np.stack([oracle_np.temporal_maxpool_row(r, w) for r in rows])[:, a:b]
+        ok = ok and np.array_equal(got, want)
+        taps = rng.uniform(-1, 1, (1, w))
+
+        def conv(ext, mode):
+            return torch.from_numpy(oracle_np.temporal_conv1d(ext.numpy(), np.repeat(taps, ext.shape[0], 0), mode))
+        for mode, pad in (("zero", 0.0), ("edge", None)):
+            got = frame_sharded_window_op(local, h, lambda e: conv(e, mode), pad_value=pad).numpy()
+            want = oracle_np.temporal_conv1d(rows, np.repeat(taps, rows.shape[0], 0), mode)[:, a:b]
+            ok = ok and np.array_equal(got, want)
+    with open(os.path.join(out_dir, "rank%d" % rank), "w") as f:
+        f.write("ok" if ok else "bad")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_temporal_sharding_gloo(tmp_path, world):
+    """BASELINE config 4's two splits: by tubelet (+ gather) and by frame with a halo of
+    w//2 columns; the window op is the NumPy oracle, so the result must equal the unsharded one bit for bit."""
+    port = _free_port()
+    mp.spawn(_temporal_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(os.path.join(str(tmp_path), "rank%d" % r)).read() == "ok"
+
+
+def test_temporal_sharding_single_process():
+    """Without a process group the helpers degenerate to the plain op / identity."""
+    from oracle import oracle_np
+    from vdetlib_b200.dist import ShardedTemporalRows, frame_sharded_window_op
+    rows = np.random.default_rng(2).uniform(-1, 1, (4, 20))
+    sh = ShardedTemporalRows(4)
+    assert (sh.start, sh.stop) == (0, 4) and sh.gather(torch.from_numpy(rows)).numpy() is not None
+
+    def maxpool(ext):
+        return torch.from_numpy(np.stack([oracle_np.temporal_maxpool_row(r, 7) for r in ext.numpy()]))
+    got = frame_sharded_window_op(torch.from_numpy(rows), 3, maxpool, pad_value=-1e5).numpy()
+    assert np.array_equal(got, np.stack([oracle_np.temporal_maxpool_row(r, 7) for r in rows]))
+    with pytest.raises(ValueError):
+        frame_sharded_window_op(torch.from_numpy(rows[:, :2]), 3, maxpool, pad_value=-1e5)

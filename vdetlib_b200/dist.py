@@ -175,3 +175,71 @@ def sharded_vid_nms(dets_local, thresh, row_offset, group=None):
     cat_r = torch.cat([all_r[r * cap:r * cap + counts[r]] for r in range(world)])
     _, merged = ops.sort_by_score_desc(cat_s, cat_r)
     return merged
+
+
+# ------------------------------------------------------------------------------------------
+# temporal stages (BASELINE config 4): rows = (tubelet, class) score sequences
+# ------------------------------------------------------------------------------------------
+class ShardedTemporalRows(object):
+    """Sharding BY TUBELET: every rank owns a contiguous range of rows and runs completion / max-pool /
+    conv on it with no communication (the preferred split: rows outnumber ranks by orders of magnitude,
+    and score completion needs a tubelet's whole frame axis).  ``gather`` reassembles the full block on
+    every rank when a consumer needs it (one all-gather, shards padded to the largest)."""
+
+    def __init__(self, n_rows, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_rows = int(n_rows)
+        self.spans = [shard_range(self.n_rows, self.world, r) for r in range(self.world)]
+        self.start, self.stop = self.spans[self.rank]
+
+    def local(self, rows):
+        """This rank's slice of a full [n_rows, ...] array / tensor."""
+        return rows[self.start:self.stop]
+
+    def gather(self, local_rows):
+        """[stop-start, L] on every rank -> [n_rows, L] on every rank."""
+        if local_rows.shape[0] != self.stop - self.start:
+            raise ValueError("gather: expected %d local rows" % (self.stop - self.start))
+        if self.world == 1:
+            return local_rows
+        cap = max(b - a for a, b in self.spans)
+        send = local_rows.new_zeros((cap,) + tuple(local_rows.shape[1:]))
+        send[:local_rows.shape[0]] = local_rows
+        recv = local_rows.new_empty((self.world * cap,) + tuple(local_rows.shape[1:]))
+        dist.all_gather_into_tensor(recv, send, group=self.group)
+        return torch.cat([recv[r * cap:r * cap + (b - a)] for r, (a, b) in enumerate(self.spans)])
+
+
+def frame_sharded_window_op(local_cols, half_window, op, pad_value=None, group=None):
+    """Sharding BY FRAME for the window stages (temporal max-pool / conv): every rank holds the columns
+    (frames) [f0, f1) of ALL rows and needs ``half_window`` columns from each neighbour -- the same
+    single boundary all-gather as the link, payload rows x 2h values per rank.
+
+    ``local_cols`` [rows, L_r] (L_r >= half_window on every rank); ``op(ext)`` maps the haloed block
+    [rows, h + L_r + h] to an output of the same shape (e.g. ``ops.temporal_maxpool(ext, w)``); the h
+    columns beyond the video's two ends are filled with ``pad_value`` when given (max-pool: -1e5, conv
+    with zero padding: 0), otherwise with the nearest edge column.  Returns [rows, L_r]."""
+    h = int(half_window)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    rows, L = local_cols.shape
+    if h == 0:
+        return op(local_cols)
+    if L < h:
+        raise ValueError("frame_sharded_window_op: a shard of %d frames is shorter than the halo %d" % (L, h))
+    edge = torch.cat([local_cols[:, :h], local_cols[:, L - h:]], dim=1).contiguous()       # [rows, 2h]
+    if world > 1:
+        recv = edge.new_empty((world,) + tuple(edge.shape))
+        dist.all_gather_into_tensor(recv.view(world * rows, 2 * h), edge, group=group)
+    else:
+        recv = edge.unsqueeze(0)
+
+    def outside(col):
+        return local_cols.new_full((rows, h), pad_value) if pad_value is not None else col.expand(rows, h)
+
+    left = recv[rank - 1][:, h:] if rank > 0 else outside(local_cols[:, :1])
+    right = recv[rank + 1][:, :h] if rank < world - 1 else outside(local_cols[:, L - 1:])
+    ext = torch.cat([left, local_cols, right], dim=1).contiguous()
+    return op(ext)[:, h:h + L]
