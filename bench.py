@@ -123,6 +123,17 @@ def _ref_frames(job):
     return F * N
 
 
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_baseline(sample_frames=1500):
     """Single-thread reference path on a bounded sample (rank 0, N=1 only)."""
     from vdetlib_b200 import synth
@@ -133,6 +144,7 @@ def cpu_baseline(sample_frames=1500):
     n = _ref_frames((b, s[:sample_frames]))
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": "boxes/s", "cores": 1, "kind": _REF["kind"],
+            "host": {"cpu_model": cpu_model(), "cpu_count": os.cpu_count()},
             "sample": "%d frames x %d boxes x %d classes: utils/nms.pyx nms (%s) per (frame,class) + C port of "
                       "the link per frame pair, one thread, %.1f s" % (sample_frames, N_BOXES, N_CLASSES,
                                                                        "compiled from the reference" if _REF["kind"] == "reference" else "C restatement", dt)}
@@ -168,6 +180,7 @@ def run_reference(args):
                                "each step = a %d-frame sample of it" % (T_FRAMES, N_BOXES, N_CLASSES, NMS_THRESH, F),
                    "frames_per_step": F},
         "cpu_baseline": {"value": value, "unit": "boxes/s", "cores": cores, "kind": _REF["kind"],
+                         "host": {"cpu_model": cpu_model(), "cpu_count": os.cpu_count()},
                          "sample": "%d frames per step over %d processes (multiprocessing, the reference's only "
                                    "parallel primitive, utils/common.py:358-359)" % (F, cores)},
         "e2e": {"value": value, "unit": "boxes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
