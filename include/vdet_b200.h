@@ -97,6 +97,8 @@ int         vdet_host_copy_stream(void* dst, const void* src, size_t bytes);
  * max_seg_len: an upper bound of the longest frame (chooses the kernel variant): <= 1024 keeps the
  * frame's bit matrix in shared memory, <= 2048 uses `ws` (vdet_nms_frames_workspace_bytes);
  * longer frames are handled by the drop-in entry points below (any length, one class).
+ * Measurement hook (not part of the contract): the environment variable VDET_NMS_PER_SM caps the
+ * resident CTAs per SM of the <= 1024-box variant (tools/nms_time.py).
  * ------------------------------------------------------------------------------------- */
 size_t vdet_nms_frames_workspace_bytes(int max_seg_len, int n_classes, int device);
 int vdet_nms_frames_f32(const float* boxes, int box_ld,
