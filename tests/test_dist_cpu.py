@@ -133,3 +133,44 @@ def test_temporal_sharding_single_process():
     assert np.array_equal(got, np.stack([oracle_np.temporal_maxpool_row(r, 7) for r in rows]))
     with pytest.raises(ValueError):
         frame_sharded_window_op(torch.from_numpy(rows[:, :2]), 3, maxpool, pad_value=-1e5)
+
+
+def _vid_nms_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import c_oracle
+    from vdetlib_b200 import ops, synth
+    from vdetlib_b200.dist import shard_range, sharded_vid_nms
+    # the two kernels behind sharded_vid_nms, replaced by the oracle on CPU tensors: what runs here is the
+    # cross-rank merge (count exchange, padded all-gathers, global stable order)
+    ops.vid_nms = lambda dets, thresh: torch.tensor(c_oracle.vid_nms(dets.numpy(), thresh), dtype=torch.int64)
+
+    def sort_desc(scores, ids):
+        order = np.argsort(-scores.numpy(), kind="stable")
+        return scores[torch.from_numpy(order)], ids[torch.from_numpy(order)]
+    ops.sort_by_score_desc = sort_desc
+    T, N = 7, 40                                                    # uneven shards at world 2 and 3
+    b, s = synth.boxes_scores(T, N, 1, seed=21)
+    sc = s[:, :, 0] + np.arange(T)[:, None] * 1e-5                  # unique across the video
+    sc[5] = sc[2]                                                   # ... except two frames with equal scores
+    dets = np.concatenate([np.repeat(np.arange(1, T + 1), N)[:, None], b.reshape(-1, 4), sc.reshape(-1, 1)],
+                          axis=1).astype(np.float32)
+    a, e = shard_range(T, world, rank)
+    got = sharded_vid_nms(torch.from_numpy(dets[a * N:e * N]), 0.3, a * N).numpy().tolist()
+    want = c_oracle.vid_nms(dets, 0.3)
+    with open(os.path.join(out_dir, "rank%d" % rank), "w") as f:
+        f.write("ok" if got == want else "bad %d %d" % (len(got), len(want)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_vid_nms_merge_gloo(tmp_path, world):
+    """vid_nms of a video sharded by frame: suppression is local, the reference's GLOBAL
+    descending-score keep order (ties: ascending row) comes from one merge across ranks."""
+    port = _free_port()
+    mp.spawn(_vid_nms_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(os.path.join(str(tmp_path), "rank%d" % r)).read() == "ok"
