@@ -47,3 +47,20 @@ def test_protocol_helpers():
     # top_detections / frame_top_detections rank on the GPU: covered by tests/test_gpu_temporal_tubelet.py
     dp = {"video": "v", "detections": [{"frame": 1, "scores": [{"class_index": 1, "score": 0.1}]}]}
     assert protocol.top_detections(dp, 5, 1) == dp                 # fewer than top_num: shallow copy (:331-332)
+
+
+def test_adapters_refuse_to_run_without_a_gpu():
+    """No CPU fallback: the device every adapter allocates on is CUDA or nothing (the CPU runs of
+    tests/test_adapters_cpu.py swap the operators for the oracle explicitly)."""
+    import pytest
+    import torch
+    from vdetlib_b200 import ops
+    from vdetlib_b200.utils import cython_nms, common
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError):
+        ops.default_device()
+    with pytest.raises(RuntimeError):
+        cython_nms.nms(np.zeros((3, 5), np.float32), 0.3)
+    with pytest.raises(RuntimeError):
+        common.iou(np.zeros((2, 4)), np.zeros((2, 4)))

@@ -14,6 +14,13 @@ from . import _lib
 MISSING = -1e5    # utils/protocol.py:459, vdet/tubelet_cls.py:344,402
 
 
+def default_device():
+    """The CUDA device the adapters allocate on.  There is no CPU path: without a GPU this raises."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("vdetlib_b200 needs a CUDA device (there is no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -454,4 +461,4 @@ def sort_by_score_desc(scores, ids):
 def to_device(array, dtype=None, device=None):
     """numpy / array-like -> CUDA tensor on the current device."""
     a = np.ascontiguousarray(array, dtype=dtype)
-    return torch.from_numpy(a).to(device or torch.device("cuda", torch.cuda.current_device()))
+    return torch.from_numpy(a).to(device or default_device())

@@ -22,6 +22,7 @@ def iou(boxes1, boxes2):
         raise IndexError("too many indices for array")
     if b1.shape[1] < 4 or b2.shape[1] < 4:
         raise IndexError("index 3 is out of bounds for axis 1")
-    a = torch.from_numpy(np.ascontiguousarray(b1[:, :4])).cuda()
-    b = torch.from_numpy(np.ascontiguousarray(b2[:, :4])).cuda()
+    dev = ops.default_device()
+    a = torch.from_numpy(np.ascontiguousarray(b1[:, :4])).to(dev)
+    b = torch.from_numpy(np.ascontiguousarray(b2[:, :4])).to(dev)
     return ops.iou_matrix(a, b).cpu().numpy()

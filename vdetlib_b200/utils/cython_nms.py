@@ -27,7 +27,7 @@ def _typed_buffer(a, name, ncol):
         raise ValueError("Buffer dtype mismatch, expected 'float32_t' but got '%s'" % a.dtype.name)
     if a.shape[1] < ncol:
         raise IndexError("index %d is out of bounds for axis 1 with size %d" % (ncol - 1, a.shape[1]))
-    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return torch.from_numpy(np.ascontiguousarray(a)).to(ops.default_device())
 
 
 def nms(dets, thresh):

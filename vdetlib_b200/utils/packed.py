@@ -409,7 +409,8 @@ class PackedDets(object):
     def device_tensors(self, device=None):
         """Frame-grouped CUDA tensors ``(boxes, scores, seg_offsets, max_seg_len, order)``."""
         import torch
-        dev = device or torch.device("cuda", torch.cuda.current_device())
+        from .. import ops
+        dev = device or ops.default_device()
         b, s, off, order, n = self.grouped_f32()
         return (torch.from_numpy(b).to(dev), torch.from_numpy(s).to(dev), torch.from_numpy(off).to(dev), n, order)
 
@@ -628,7 +629,8 @@ class PackedTubelets(object):
     @staticmethod
     def _to_dev(a, device):
         import torch
-        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        from .. import ops
+        dev = device if device is not None else ops.default_device()
         return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
     def complete_scores_(self, device=None):

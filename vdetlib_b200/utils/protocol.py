@@ -75,8 +75,9 @@ def top_detections(det_proto, top_num, class_index):
     if len(det_proto['detections']) < top_num:
         return copy.copy(det_proto)
     scores = _class_scores(det_proto, class_index)                     # Python floats -> float64 keys
-    ids = torch.arange(len(scores), dtype=torch.int64, device="cuda")
-    order = ops.sort_by_score_desc(torch.from_numpy(scores).cuda(), ids)[1].cpu().tolist()
+    dev = ops.default_device()
+    ids = torch.arange(len(scores), dtype=torch.int64, device=dev)
+    order = ops.sort_by_score_desc(torch.from_numpy(scores).to(dev), ids)[1].cpu().tolist()
     dets = det_proto['detections']
     return {'video': det_proto['video'], 'detections': [dets[i] for i in order[:top_num]]}
 
@@ -96,8 +97,9 @@ def frame_top_detections(det_proto, top_num, class_index):
     frames = np.asarray([d['frame'] for d in dets], dtype=np.float32)
     if not np.array_equal(frames.astype(np.float64), np.asarray([d['frame'] for d in dets], dtype=np.float64)):
         raise NotImplementedError("frame ids must be exactly representable in float32 (|frame| < 2^24)")
-    row_ids, seg_off, seg_frame, _ = ops.segment_by_frame(torch.from_numpy(frames).cuda(), None,
-                                                           torch.from_numpy(scores).cuda())
+    dev = ops.default_device()
+    row_ids, seg_off, seg_frame, _ = ops.segment_by_frame(torch.from_numpy(frames).to(dev), None,
+                                                           torch.from_numpy(scores).to(dev))
     row_ids, seg_off = row_ids.cpu().numpy(), seg_off.cpu().numpy()
     seg_of = {float(f): s for s, f in enumerate(seg_frame.cpu().tolist())}
     for frame_id in frame_idx:
@@ -150,9 +152,10 @@ def tubelets_overlap(tubelets_proto, annot_proto, class_idx):
                if frames else np.zeros((0, 4)))
         tb = np.asarray([b['bbox'] for b in boxes], dtype=np.float64).reshape(-1, 4)
         seg = np.asarray([seg_of.get(b['frame'], -1) for b in boxes], dtype=np.int32)
-        dummy = torch.zeros(max(len(ann), 1), dtype=torch.float64, device="cuda")
-        arg, best = ops.spatial_maxpool(torch.from_numpy(tb).cuda(), torch.from_numpy(seg).cuda(),
-                                        torch.from_numpy(ann).cuda(), dummy, torch.from_numpy(seg_off).cuda(),
+        dev = ops.default_device()
+        dummy = torch.zeros(max(len(ann), 1), dtype=torch.float64, device=dev)
+        arg, best = ops.spatial_maxpool(torch.from_numpy(tb).to(dev), torch.from_numpy(seg).to(dev),
+                                        torch.from_numpy(ann).to(dev), dummy, torch.from_numpy(seg_off).to(dev),
                                         0.0, _lib.POOL_MAX_IOU)
         arg, best = arg.cpu().numpy(), best.cpu().numpy()
         for b, a, v in zip(boxes, arg, best):

@@ -25,7 +25,7 @@ class _GreedyState(object):
 
     def __init__(self, det_info):
         self.m = len(det_info)
-        self.det_info = torch.from_numpy(np.ascontiguousarray(det_info, dtype=np.float32)).cuda()
+        self.det_info = torch.from_numpy(np.ascontiguousarray(det_info, dtype=np.float32)).to(ops.default_device())
         self.keep = torch.ones(max(self.m, 1), dtype=torch.uint8, device=self.det_info.device)
         self.status = ops.new_status(self.det_info.device)
         if self.m:

@@ -32,7 +32,8 @@ def _pack_rows(rows, fill=0.0):
     for i, r in enumerate(rows):
         if len(r):
             buf[i, :len(r)] = r
-    return torch.from_numpy(buf).cuda(), torch.from_numpy(lens).cuda(), lens
+    dev = ops.default_device()
+    return torch.from_numpy(buf).to(dev), torch.from_numpy(lens).to(dev), lens
 
 
 def _pool_on_gpu(tub_boxes, tub_frames, frame_dets, overlap_thres, mode):
@@ -51,10 +52,11 @@ def _pool_on_gpu(tub_boxes, tub_frames, frame_dets, overlap_thres, mode):
         det_boxes = np.zeros((0, 4)); det_scores = np.zeros((0,))
     tb = np.asarray(tub_boxes, dtype=np.float64).reshape(-1, 4)
     seg = np.asarray([seg_of.get(f, -1) for f in tub_frames], dtype=np.int32)
+    dev = ops.default_device()
     arg, score = ops.spatial_maxpool(
-        torch.from_numpy(tb).cuda(), torch.from_numpy(seg).cuda(),
-        torch.from_numpy(det_boxes).cuda(), torch.from_numpy(det_scores).cuda(),
-        torch.from_numpy(seg_off.astype(np.int32)).cuda(), overlap_thres, mode)
+        torch.from_numpy(tb).to(dev), torch.from_numpy(seg).to(dev),
+        torch.from_numpy(det_boxes).to(dev), torch.from_numpy(det_scores).to(dev),
+        torch.from_numpy(seg_off.astype(np.int32)).to(dev), overlap_thres, mode)
     arg = arg.cpu().numpy().astype(np.int64)
     score = score.cpu().numpy()
     base = np.where(seg >= 0, seg_off[np.maximum(seg, 0)], 0)
@@ -157,7 +159,7 @@ def score_conv_cls(score_proto, net):
             else:
                 raise KeyError(name)
         dev, lens_dev, lens = _pack_rows(rows)
-        y = ops.temporal_conv1d(dev, torch.from_numpy(taps.reshape(1, -1)).cuda(), net.pad_mode, lens_dev)
+        y = ops.temporal_conv1d(dev, torch.from_numpy(taps.reshape(1, -1)).to(dev.device), net.pad_mode, lens_dev)
         total = y if total is None else total + y
     out = (total + net.bias).cpu().numpy()
     for t, row in zip(tubelets, out):
@@ -329,7 +331,7 @@ def score_proto_interpolation(score_proto, vid_proto):
                 max_idx = max_frames
             dense_first.append(min_idx)
             dense_off.append(dense_off[-1] + max_idx - min_idx + 1)
-        dev = torch.device("cuda", torch.cuda.current_device())
+        dev = ops.default_device()
         out = ops.tubelet_interpolate(
             torch.tensor(xs, dtype=torch.float64, device=dev), torch.tensor(ys, dtype=torch.float64, device=dev),
             torch.tensor(knot_off, dtype=torch.int32, device=dev), torch.tensor(dense_first, dtype=torch.int32, device=dev),

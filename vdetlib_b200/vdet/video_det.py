@@ -41,7 +41,7 @@ def threshold_topk_frames(scores, boxes, thresh=0.05, max_per_image=100):
     scores = np.ascontiguousarray(scores, dtype=np.float32)
     boxes = np.asarray(boxes, dtype=np.float32)
     T, R, C = scores.shape
-    dev_scores = torch.from_numpy(scores.reshape(T * R, C)).cuda()
+    dev_scores = torch.from_numpy(scores.reshape(T * R, C)).to(ops.default_device())
     seg = ops.seg_offsets_uniform(T, R, dev_scores.device)
     idx, cnt = ops.threshold_topk(dev_scores, seg, R, thresh, max_per_image)
     idx = idx.cpu().numpy()
@@ -136,7 +136,7 @@ class VideoPostProcessor(object):
     def __init__(self, n_frames, n_boxes, n_classes, nms_thresh=0.3, device=None, n_chunks=8, n_slots=2):
         self.T, self.N, self.C = int(n_frames), int(n_boxes), int(n_classes)
         self.nms_thresh = float(nms_thresh)
-        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.device = device or ops.default_device()
         T, N, C = self.T, self.N, self.C
         rows = T * N
         dev = self.device
