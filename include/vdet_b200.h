@@ -74,6 +74,10 @@ int         vdet_set_reserved_sms(int n);
  * run at about half the PCIe rate on the measured host (profiles/r01_pcie.md); streamed lines are
  * in DRAM when the copy engine asks for them.  Plain host memory in and out, no CUDA call. */
 int         vdet_host_copy_stream(void* dst, const void* src, size_t bytes);
+/* The same over `n_threads` host threads, each streaming a range of whole 64-byte lines (<= 0: half the
+ * hardware threads, at most 8, for copies of 4 MB and more, else 1).  One core streams ~10 GB/s; staging a 41 MB shard with one
+ * thread takes longer than the GPU needs for the whole step. */
+int         vdet_host_copy_stream_mt(void* dst, const void* src, size_t bytes, int n_threads);
 
 /* ---------------------------------------------------------------------------------------
  * Per-frame greedy NMS on class-shared boxes.

@@ -72,3 +72,23 @@ def test_no_cpu_fallback_in_product():
     from vdetlib_b200.utils import cython_nms
     with pytest.raises(ValueError):
         cython_nms.nms(np.zeros((2, 5), np.float64), 0.3)      # dtype check precedes any device work
+
+
+def test_host_copy_stream_threads_and_alignment():
+    """vdet_host_copy_stream(_mt): plain host memory in and out (no CUDA call): every byte lands, nothing
+    outside the destination range is touched, for any alignment and thread count."""
+    import numpy as np
+    from vdetlib_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 15, 63, 64, 65, 4095, 4096, 100003, 1200007):
+        src = rng.integers(0, 256, n + 64, dtype=np.uint8)
+        for so, do in ((0, 0), (1, 3), (7, 16), (0, 61)):
+            for th in (1, 2, 3, 8, 0):
+                dst = np.full(n + 128, 0xAB, np.uint8)
+                assert lib.vdet_host_copy_stream_mt(dst.ctypes.data + do, src.ctypes.data + so, n, th) == 0
+                assert np.array_equal(dst[do:do + n], src[so:so + n]), (n, so, do, th)
+                assert np.all(dst[:do] == 0xAB) and np.all(dst[do + n:] == 0xAB), (n, so, do, th)
+    dst = np.zeros(64, np.uint8)
+    assert lib.vdet_host_copy_stream(dst.ctypes.data, src.ctypes.data, 64) == 0 and np.array_equal(dst, src[:64])
+    assert lib.vdet_host_copy_stream_mt(None, src.ctypes.data, 8, 2) == _lib.ERR_INVALID

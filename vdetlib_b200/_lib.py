@@ -28,6 +28,7 @@ SIGNATURES = {
     "vdet_sm_count": (_i32, [_i32]),
     "vdet_set_reserved_sms": (_i32, [_i32]),
     "vdet_host_copy_stream": (_i32, [_vp, _vp, _sz]),
+    "vdet_host_copy_stream_mt": (_i32, [_vp, _vp, _sz, _i32]),
     "vdet_nms_frames_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "vdet_nms_frames_f32": (_i32, [_vp, _i32, _vp, _i64, _i64, _vp, _i32, _i32, _vp, _i32, _f64,
                                    _vp, _vp, _vp, _i64, _i32, _vp, _vp, _sz, _vp]),

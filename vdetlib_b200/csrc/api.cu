@@ -5,6 +5,8 @@
 #include "common.cuh"
 #include <emmintrin.h>
 #include <cstring>
+#include <thread>
+#include <vector>
 
 namespace vdet {
 
@@ -54,22 +56,9 @@ int max_optin_smem_cached() {
     return v > 0 ? v : 227 * 1024;
 }
 
-}  // namespace vdet
-
-extern "C" {
-
-int vdet_abi_version(void) { return VDET_ABI_VERSION; }
-
-const char* vdet_last_error(void) { return vdet::g_err; }
-
-int vdet_host_copy_stream(void* dst, const void* src, size_t bytes) {
-    if (bytes == 0) return VDET_OK;
-    if (dst == nullptr || src == nullptr) {
-        vdet::set_error("host_copy_stream: null pointer");
-        return VDET_ERR_INVALID;
-    }
-    unsigned char* d = static_cast<unsigned char*>(dst);
-    const unsigned char* s = static_cast<const unsigned char*>(src);
+// Non-temporal copy of one byte range (16-byte streaming stores, plain copies for the unaligned ends),
+// fenced before returning so that the stores are globally visible when the caller hands the buffer to a DMA.
+void copy_stream_range(unsigned char* d, const unsigned char* s, size_t bytes) {
     size_t head = (16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15;     // stores must be 16-byte aligned
     if (head > bytes) head = bytes;
     memcpy(d, s, head);
@@ -87,6 +76,54 @@ int vdet_host_copy_stream(void* dst, const void* src, size_t bytes) {
     for (; i < nvec; ++i) _mm_stream_si128(dv + i, _mm_loadu_si128(sv + i));
     memcpy(d + nvec * 16, s + nvec * 16, bytes - nvec * 16);
     _mm_sfence();
+}
+
+}  // namespace vdet
+
+extern "C" {
+
+int vdet_abi_version(void) { return VDET_ABI_VERSION; }
+
+const char* vdet_last_error(void) { return vdet::g_err; }
+
+int vdet_host_copy_stream(void* dst, const void* src, size_t bytes) {
+    return vdet_host_copy_stream_mt(dst, src, bytes, 1);
+}
+
+int vdet_host_copy_stream_mt(void* dst, const void* src, size_t bytes, int n_threads) {
+    if (bytes == 0) return VDET_OK;
+    if (dst == nullptr || src == nullptr) {
+        vdet::set_error("host_copy_stream: null pointer");
+        return VDET_ERR_INVALID;
+    }
+    if (n_threads <= 0) {                                   // auto: one core moves ~10 GB/s, the DRAM bus several times that
+        const unsigned hw = std::thread::hardware_concurrency() / 2;     // physical cores, roughly
+        n_threads = (int)(hw == 0 ? 1 : (hw > 8 ? 8 : hw));
+        if (bytes < (size_t)(4u << 20)) n_threads = 1;      // not worth the thread start-up
+    }
+    if (n_threads > 64) n_threads = 64;
+    unsigned char* d = static_cast<unsigned char*>(dst);
+    const unsigned char* s = static_cast<const unsigned char*>(src);
+    if (n_threads == 1 || bytes < (size_t)n_threads * 4096) {
+        vdet::copy_stream_range(d, s, bytes);
+        return VDET_OK;
+    }
+    // ranges start on 64-byte lines of the destination (a line is never shared by two threads)
+    const size_t head = (64 - (reinterpret_cast<uintptr_t>(d) & 63)) & 63;
+    const size_t lines = (bytes - head) / 64;
+    const size_t per = (lines + n_threads - 1) / n_threads;
+    std::vector<std::thread> pool;
+    pool.reserve(n_threads - 1);
+    for (int t = 1; t < n_threads; ++t) {
+        const size_t l0 = per * (size_t)t, l1 = (l0 + per < lines) ? l0 + per : lines;
+        if (l0 >= l1) break;
+        const size_t b0 = head + l0 * 64;
+        const size_t b1 = (l1 == lines) ? bytes : head + l1 * 64;          // the last range takes the tail
+        pool.emplace_back(vdet::copy_stream_range, d + b0, s + b0, b1 - b0);
+    }
+    const size_t first_end = (per < lines) ? head + per * 64 : bytes;
+    vdet::copy_stream_range(d, s, first_end);                               // this thread: head + first range
+    for (auto& th : pool) th.join();
     return VDET_OK;
 }
 

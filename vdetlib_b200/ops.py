@@ -73,14 +73,16 @@ def raise_for_status(status):
     return raise_for_status_word(status.item())
 
 
-def host_copy_stream(dst_pinned, src):
-    """Fill a (pinned) host tensor from a C-contiguous NumPy array with non-temporal stores."""
+def host_copy_stream(dst_pinned, src, threads=0):
+    """Fill a (pinned) host tensor from a C-contiguous NumPy array with non-temporal stores, over
+    ``threads`` host threads (0: up to 8 for copies of 4 MB and more)."""
     if dst_pinned.device.type != "cpu" or not dst_pinned.is_contiguous():
         raise ValueError("host_copy_stream: destination must be a contiguous host tensor")
     nbytes = dst_pinned.numel() * dst_pinned.element_size()
     if not src.flags["C_CONTIGUOUS"] or src.nbytes != nbytes:
         raise ValueError("host_copy_stream: source must be C-contiguous with %d bytes" % nbytes)
-    _lib.check(_lib.load().vdet_host_copy_stream(dst_pinned.data_ptr(), src.ctypes.data, nbytes), "host_copy_stream")
+    _lib.check(_lib.load().vdet_host_copy_stream_mt(dst_pinned.data_ptr(), src.ctypes.data, nbytes, int(threads)),
+               "host_copy_stream")
 
 
 def seg_offsets_uniform(n_frames, n_per_frame, device):
