@@ -177,3 +177,40 @@ def test_file_round_trip(tmp_path, fake_ops):
     assert packed.proto_load_packed(p) == sp                         # the source file is untouched
     with pytest.raises(ValueError):
         packed.PackedTubelets(*packed.pack_proto(helpers.golden_protos()["det"]))
+
+
+def test_packed_spatial_max_pooling_matches_the_reference_golden(monkeypatch):
+    """The whole tubelet-scoring chain on packed data -- pool_dets_ + complete_scores_ -- against the protos the
+    reference's dets_spatial_max_pooling / raw_dets_spatial_max_pooling produced (no dict walk over the dets)."""
+    import kernel_double
+    dev = kernel_double.install(monkeypatch)
+    p = helpers.golden_protos()
+    vid, det, trk, out = p["vid"], p["det"], p["track"], p["out"]
+    dets = packed.PackedDets.from_det_proto(det)
+    assert dets.boxes_are_int
+    for cls in (1, 3):
+        for suffix, thr in (("", 0.7), ("_05", 0.5)):
+            pt = packed.PackedTubelets.for_pooling(vid, copy.deepcopy(trk), cls, thr)
+            pt.pool_dets_(dets, cls, vid, thr, device=dev).complete_scores_(device=dev)
+            got = pt.to_score_proto()
+            want = out["smp_%d%s" % (cls, suffix)]
+            assert got == want and json.dumps(got) == json.dumps(want)
+    # raw detections (frame -> (boxes, zs) arrays): float boxes come back as floats
+    from vdetlib_b200 import synth
+    boxes, scores = synth.boxes_scores(8, 40, 5, seed=4000, integer=True, frame_offset=1e-4)
+    f2d = {t + 1: (boxes[t].astype(np.float64), scores[t].astype(np.float64)) for t in range(8)}
+    f2d[9] = (np.zeros((0, 4)), np.zeros((0, 5)))                    # a frame without boxes is skipped (:513)
+    raw = packed.PackedDets.from_frame_to_det(vid['video'], f2d)
+    pt = packed.PackedTubelets.for_pooling(vid, copy.deepcopy(trk), 2)
+    pt.pool_dets_(raw, 2, vid, device=dev).complete_scores_(device=dev)
+    got = pt.to_score_proto()
+    assert got == out["raw_smp_2"] and json.dumps(got) == json.dumps(out["raw_smp_2"])
+    # the same through the side-car files
+    import os
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        dets.save(os.path.join(d, "dets.vdetpk"))
+        again = packed.PackedDets.load(os.path.join(d, "dets.vdetpk"))
+        pt = packed.PackedTubelets.for_pooling(vid, copy.deepcopy(trk), 1)
+        pt.pool_dets_(again, 1, vid, device=dev).complete_scores_(device=dev)
+        assert pt.to_score_proto() == out["smp_1"] and json.dumps(pt.to_score_proto()) == json.dumps(out["smp_1"])

@@ -320,14 +320,17 @@ class PackedDets(object):
             raise ValueError("PackedDets: frames / boxes / scores disagree on the number of detections")
         self.classes = list(classes) if classes is not None else None
         self.class_index = list(class_index) if class_index is not None else list(range(self.scores.shape[1]))
+        self.boxes_are_int = False      # every bbox number of the source proto was a Python int
 
     # ---- constructors ----------------------------------------------------------------------
     @classmethod
     def from_packed(cls, meta, arrays):
         """From a packed det proto (``load_packed`` of a file written by ``proto_dump_packed``)."""
         if meta.get("kind") == "dets":
-            return cls(meta["video"], arrays["frames"], arrays["boxes"], arrays["scores"],
-                       meta.get("classes"), meta.get("class_index"))
+            out = cls(meta["video"], arrays["frames"], arrays["boxes"], arrays["scores"],
+                      meta.get("classes"), meta.get("class_index"))
+            out.boxes_are_int = bool(meta.get("boxes_are_int", False))
+            return out
         if meta.get("kind") != "det":
             raise ValueError("not a packed det proto")
         cols = meta["detections"]["cols"]
@@ -335,8 +338,10 @@ class PackedDets(object):
             if key not in cols or cols[key]["t"] != want or not cols[key]["all"]:
                 raise ValueError("packed det proto has no regular %r column" % key)
         sc = cols["scores"]
-        return cls(meta["top"].get("video"), arrays["det.frame"], arrays["det.bbox"], arrays["det.scores"],
-                   sc["classes"], sc["class_index"])
+        out = cls(meta["top"].get("video"), arrays["det.frame"], arrays["det.bbox"], arrays["det.scores"],
+                  sc["classes"], sc["class_index"])
+        out.boxes_are_int = cols["bbox"]["int"] == "all"
+        return out
 
     @classmethod
     def from_det_proto(cls, det_proto):
@@ -417,7 +422,7 @@ class PackedDets(object):
     # ---- file --------------------------------------------------------------------------------
     def save(self, path):
         save_packed(path, {"kind": "dets", "video": self.video, "classes": self.classes,
-                           "class_index": self.class_index},
+                           "class_index": self.class_index, "boxes_are_int": bool(self.boxes_are_int)},
                     {"frames": self.frames, "boxes": self.boxes, "scores": self.scores})
 
     @classmethod
@@ -625,7 +630,77 @@ class PackedTubelets(object):
                 col["int"] = "map"
                 self.arrays[name + "__int"] = np.packbits(ints)
 
+    @classmethod
+    def for_pooling(cls, vid_proto, track_proto, class_idx, overlap_thres=0.7):
+        """The score-proto shell dets_spatial_max_pooling starts from (vdet/tubelet_cls.py:306-311): video,
+        method name, tubelets of ``track_proto`` with ``det_score = -1e5`` (utils/protocol.py:448-464)."""
+        from .protocol import tubelets_proto_from_tracks_proto
+        assert vid_proto['video'] == track_proto['video']
+        return cls.from_score_proto({
+            'video': vid_proto['video'], 'method': "spatial_max_pooling_IOU_{}".format(overlap_thres),
+            'tubelets': tubelets_proto_from_tracks_proto(track_proto['tracks'], class_idx)})
+
+    def _write_rows(self, key, rows, values, ints):
+        """Overwrite rows ``rows`` of column ``key`` (num: [n], vec: [n,w]) keeping the int/float type map exact."""
+        col = self._col(key)
+        name = "tub." + key
+        arr = np.array(self.arrays[name], dtype=np.float64, copy=True)
+        arr[rows] = values
+        self.arrays[name] = arr
+        width = 1 if arr.ndim == 1 else arr.shape[1]
+        if col["int"] == ("all" if ints else "none"):
+            return
+        old = col["int"]
+        if old == "map":
+            m = np.unpackbits(np.asarray(self.arrays[name + "__int"]), count=arr.size).astype(bool)
+        else:
+            m = np.full(arr.size, old == "all")
+        m = m.reshape(-1, width)
+        m[rows] = bool(ints)
+        m = m.reshape(-1)
+        self.arrays.pop(name + "__int", None)
+        if m.all():
+            col["int"] = "all"
+        elif not m.any():
+            col["int"] = "none"
+        else:
+            col["int"] = "map"
+            self.arrays[name + "__int"] = np.packbits(m)
+
     # ---- stages (GPU) ------------------------------------------------------------------------
+    def pool_dets_(self, dets, class_idx, vid_proto, overlap_thres=0.7, device=None):
+        """Spatial max-pooling of packed detections onto the tubelets, the body of dets_spatial_max_pooling /
+        raw_dets_spatial_max_pooling (vdet/tubelet_cls.py:324-347, :509-532) without a dict walk over the
+        detections: for every tubelet box on a frame of ``vid_proto`` that has detections, among the dets with
+        IoU > overlap_thres the FIRST arg-max of the class score (column ``class_idx - 1``, positional like
+        :329 / :514) gives ``det_score`` and ``bbox``; none -> ``det_score = -1e5``, bbox unchanged.  Follow with
+        ``complete_scores_()`` as the reference does (:349, :534)."""
+        from .. import _lib, ops
+        off, order, seg_frames = dets.frame_segments()
+        if not len(seg_frames) or not int(self.offsets[-1]):
+            return self
+        vid_frames = np.asarray([f['frame'] for f in vid_proto['frames']], dtype=np.int64)
+        tub_frames = self.column('frame').astype(np.int64)
+        seg = np.searchsorted(seg_frames, tub_frames)
+        seg[seg >= len(seg_frames)] = 0
+        has = (seg_frames[seg] == tub_frames) & np.isin(tub_frames, vid_frames)
+        sel = np.nonzero(has)[0]
+        if not len(sel):
+            return self
+        det_boxes = np.ascontiguousarray(dets.boxes[order])
+        det_scores = np.ascontiguousarray(dets.scores[order, class_idx - 1])
+        arg, score = ops.spatial_maxpool(
+            self._to_dev(self.column('bbox')[sel].astype(np.float64), device), self._to_dev(seg[sel].astype(np.int32), device),
+            self._to_dev(det_boxes, device), self._to_dev(det_scores, device), self._to_dev(off.astype(np.int32), device),
+            overlap_thres, _lib.POOL_ARGMAX_SCORE)
+        arg, score = arg.cpu().numpy().astype(np.int64), score.cpu().numpy()
+        hit = arg >= 0
+        new_score = np.where(hit, score, -1e5)
+        self._write_rows('det_score', sel, new_score, ints=False)
+        if hit.any():
+            self._write_rows('bbox', sel[hit], det_boxes[arg[hit]], ints=dets.boxes_are_int)
+        return self
+
     @staticmethod
     def _to_dev(a, device):
         import torch
