@@ -58,9 +58,11 @@ def threshold_topk_frames(scores, boxes, thresh=0.05, max_per_image=100):
 class _Slot(object):
     """Device inputs / outputs, pinned result buffers and the completion event of ONE in-flight step."""
 
-    def __init__(self, pp):
+    def __init__(self, pp, stage_set=0):
         T, N, C, dev = pp.T, pp.N, pp.C, pp.device
         rows = T * N
+        self.stage_set = stage_set                          # which pinned upload buffers this slot reads
+        self.h_boxes, self.h_scores = pp.h_boxes_sets[stage_set], pp.h_scores_sets[stage_set]
         self.d_boxes = torch.empty((rows, 4), dtype=torch.float32, device=dev)
         self.d_scores = torch.empty((rows, C), dtype=torch.float32, device=dev)
         self.d_idx = torch.empty(rows * C, dtype=torch.int32, device=dev)
@@ -95,7 +97,7 @@ class _Slot(object):
                         pp.nms_thresh, d_idx.data_ptr(), d_cnt.data_ptr(), d_mask.data_ptr(), r1 - r0,
                         _lib.LAYOUT_FRAME_MAJOR, self.status.data_ptr(), ws_ptr, ws_bytes)
             self.chunks.append({
-                "d_scores": d_sc, "h_scores": pp.h_scores[r0:r1], "nms_args": nms_args,
+                "d_scores": d_sc, "h_scores": self.h_scores[r0:r1], "nms_args": nms_args,
                 "d_mask": d_mask, "h_mask": self.h_mask[r0 * C:r1 * C], "d_cnt": d_cnt, "h_cnt": self.h_cnt[f0:f1],
                 "ev_in": torch.cuda.Event(), "ev_nms": torch.cuda.Event()})
 
@@ -133,7 +135,7 @@ class VideoPostProcessor(object):
     (``graph=True``): one launch per step instead of ~50 stream operations.
     """
 
-    def __init__(self, n_frames, n_boxes, n_classes, nms_thresh=0.3, device=None, n_chunks=8, n_slots=2):
+    def __init__(self, n_frames, n_boxes, n_classes, nms_thresh=0.3, device=None, n_chunks=8, n_slots=2, n_stage=1):
         self.T, self.N, self.C = int(n_frames), int(n_boxes), int(n_classes)
         self.nms_thresh = float(nms_thresh)
         self.device = device or ops.default_device()
@@ -141,8 +143,15 @@ class VideoPostProcessor(object):
         rows = T * N
         dev = self.device
         self.seg_offsets = ops.seg_offsets_uniform(T, N, dev)
-        self.h_boxes = torch.empty((rows, 4), dtype=torch.float32).pin_memory()
-        self.h_scores = torch.empty((rows, C), dtype=torch.float32).pin_memory()
+        # pinned upload buffers: one set shared by every slot (n_stage=1: the staged shard can be submitted any
+        # number of times), or one set per slot (n_stage=n_slots: shard k+1 is staged while shard k is in flight)
+        n_slots = max(1, int(n_slots))
+        if int(n_stage) not in (1, n_slots):
+            raise ValueError("n_stage must be 1 or n_slots")
+        self.n_stage = int(n_stage)
+        self.h_boxes_sets = [torch.empty((rows, 4), dtype=torch.float32).pin_memory() for _ in range(self.n_stage)]
+        self.h_scores_sets = [torch.empty((rows, C), dtype=torch.float32).pin_memory() for _ in range(self.n_stage)]
+        self.h_boxes, self.h_scores = self.h_boxes_sets[0], self.h_scores_sets[0]
         # frame ranges of the pipeline chunks
         n_chunks = max(1, min(int(n_chunks), T))
         edges = [round(k * T / n_chunks) for k in range(n_chunks + 1)]
@@ -150,7 +159,7 @@ class VideoPostProcessor(object):
         self.chunk_seg = {f1 - f0: ops.seg_offsets_uniform(f1 - f0, N, dev) for f0, f1 in self.chunks}
         self.s_in = torch.cuda.Stream(device=dev)
         self.s_out = torch.cuda.Stream(device=dev)
-        self.slots = [_Slot(self) for _ in range(max(1, int(n_slots)))]
+        self.slots = [_Slot(self, k % self.n_stage) for k in range(n_slots)]
         self._next_slot = 0
         self._graphs = {}
         self._lib = _lib.load()
@@ -215,18 +224,22 @@ class VideoPostProcessor(object):
         return res
 
     def stage(self, boxes, scores):
-        """Copy host arrays into the pinned upload buffers (not part of the timed region) with
-        streaming stores: lines written with ordinary stores stay dirty in the CPU caches and the
-        copy engine then reads them at roughly half the PCIe rate (profiles/r01_pcie.md).
-        Every step in flight reads these buffers: collect all outstanding steps before restaging."""
+        """Copy host arrays into the pinned upload buffers of the NEXT step to be submitted (not part of the
+        timed region) with streaming stores: lines written with ordinary stores stay dirty in the CPU caches and
+        the copy engine then reads them at roughly half the PCIe rate (profiles/r01_pcie.md).
+        With one staging set (``n_stage=1``) every step in flight reads these buffers: collect all outstanding
+        steps before restaging.  With a set per slot only the slot about to be reused must have been collected."""
         b = np.ascontiguousarray(boxes, dtype=np.float32).reshape(-1, 4)
         s = np.ascontiguousarray(scores, dtype=np.float32).reshape(-1, self.C)
         if b.shape[0] != self.h_boxes.shape[0] or s.shape[0] != self.h_scores.shape[0]:
             raise ValueError("stage: expected %d rows" % self.h_boxes.shape[0])
-        if any(sl.busy for sl in self.slots):
+        if not any(sl.busy for sl in self.slots):
+            self._next_slot = 0
+        target = self.slots[self._next_slot]
+        if any(sl.busy and sl.stage_set == target.stage_set for sl in self.slots):
             raise RuntimeError("stage: a submitted step still reads the staging buffers; collect() it first")
-        ops.host_copy_stream(self.h_boxes, b)
-        ops.host_copy_stream(self.h_scores, s)
+        ops.host_copy_stream(target.h_boxes, b)
+        ops.host_copy_stream(target.h_scores, s)
 
     def _enqueue(self, sl, halo, halo_fn, fork):
         """Stream operations of one staged step on slot ``sl``.  The boxes (4 floats/row) go first, so
@@ -241,7 +254,7 @@ class VideoPostProcessor(object):
             s_in.wait_stream(cur)
             s_out.wait_stream(cur)
         with torch.cuda.stream(s_in):
-            sl.d_boxes.copy_(self.h_boxes, non_blocking=True)
+            sl.d_boxes.copy_(sl.h_boxes, non_blocking=True)
             sl.ev_boxes.record(s_in)
             for ch in sl.chunks:
                 ch["d_scores"].copy_(ch["h_scores"], non_blocking=True)
