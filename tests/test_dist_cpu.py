@@ -174,3 +174,59 @@ def test_sharded_vid_nms_merge_gloo(tmp_path, world):
     mp.spawn(_vid_nms_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert open(os.path.join(str(tmp_path), "rank%d" % r)).read() == "ok"
+
+
+def _sharded_pipeline_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import cuda_fake
+    from oracle import c_oracle
+    from vdetlib_b200 import synth
+    mpatch = pytest.MonkeyPatch()
+    cuda_fake.install(mpatch)                                      # fake streams, oracle-backed launches, CPU tensors
+    from vdetlib_b200.dist import ShardedVideoPostProcessor, shard_range
+    T, N, C, thr = 4 * world, 40, 3, 0.3                          # equal shards (the processor has a fixed shape)
+    b, s = synth.boxes_scores(T, N, C, seed=12)
+    km, _, kc = c_oracle.nms_frames(b, s, thr)
+    ls, lb = c_oracle.link_f32(b)                                  # [T-1, N]: successor index inside frame t+1
+    a, e = shard_range(T, world, rank)
+    pp = ShardedVideoPostProcessor(e - a, N, C, thr, torch.device("cpu"))
+    pp.pp.stage(b[a:e], s[a:e])
+    ok = True
+    # two steps in flight through the boundary exchange, then a synchronous step
+    tickets = [pp.submit_host(), pp.submit_host()]
+    results = [{k: np.array(v, copy=True) for k, v in pp.collect(t).items()} for t in tickets]
+    results.append(pp.step_host())
+    per = e - a
+    for res in results:
+        ok = ok and np.array_equal(res["keep_mask"], km[a:e]) and np.array_equal(res["keep_cnt"], kc[a:e])
+        succ = res["succ"].reshape(per, N)
+        iou = res["link_iou"].reshape(per, N)
+        for t in range(per):
+            g = a + t                                              # global frame
+            if g < T - 1:
+                # inside the shard: packed local row of frame t+1; across the boundary: index into the halo
+                base = (t + 1) * N if t < per - 1 else 0
+                ok = ok and np.array_equal(succ[t] - base, ls[g]) and np.array_equal(iou[t], lb[g])
+            else:
+                ok = ok and np.all(succ[t] == -1)
+    with open(os.path.join(out_dir, "rank%d" % rank), "w") as f:
+        f.write("ok" if ok else "bad")
+    mpatch.undo()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_pipeline_host_logic_gloo(tmp_path, world):
+    """The frame-sharded staged step (ShardedVideoPostProcessor.submit_host / collect / step_host) across ranks
+    on the CPU harness: the boundary all-gather is real (gloo), the launches are the oracle.  Every rank's
+    shard must equal its slice of the single-process result, the last frame of a shard linking into the next
+    rank's first frame.  (The same with NCCL and the real kernels: tests/test_gpu_multi.py.)"""
+    port = _free_port()
+    mp.spawn(_sharded_pipeline_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(os.path.join(str(tmp_path), "rank%d" % r)).read() == "ok"
