@@ -111,10 +111,24 @@ def link_frames(boxes, seg_offsets, max_seg_len, halo=None, halo_row_base=0, out
     return torch.from_numpy(succ), torch.from_numpy(best)
 
 
+def _nms_frames_via(lib):
+    def nms_frames(boxes, scores, seg_offsets, thresh, max_seg_len, row_ids=None, want_mask=False,
+                   status=None, class_major=False, frame_major_out=False, out=None):
+        """ops.nms_frames in the form the sharded device step uses it: frame-major, caller's buffers."""
+        assert frame_major_out and out is not None and row_ids is None and not class_major
+        n, C = scores.shape
+        lib.vdet_nms_frames_f32(boxes.data_ptr(), 4, scores.data_ptr(), C, 1, seg_offsets.data_ptr(),
+                                seg_offsets.numel() - 1, max_seg_len, None, C, float(thresh), out[0].data_ptr(),
+                                out[1].data_ptr(), out[2].data_ptr(), n, 1, status.data_ptr(), None, 0, 0)
+        return out[0], out[1], out[2], status
+    return nms_frames
+
+
 def install(monkeypatch):
     """Patch torch.cuda / ops / _lib so that VideoPostProcessor(device=cpu) runs; returns the FakeLib."""
     from vdetlib_b200 import _lib, ops
     lib = FakeLib()
+    monkeypatch.setattr(ops, "nms_frames", _nms_frames_via(lib))
     monkeypatch.setattr(torch.cuda, "Stream", FakeStream)
     monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
     monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())

@@ -200,6 +200,10 @@ def _sharded_pipeline_worker(rank, world, port, out_dir):
     tickets = [pp.submit_host(), pp.submit_host()]
     results = [{k: np.array(v, copy=True) for k, v in pp.collect(t).items()} for t in tickets]
     results.append(pp.step_host())
+    # the device-resident step (exchange beside the NMS, then the link) on the staged shard
+    dev_res = pp.step_device(pp.pp.d_boxes, pp.pp.d_scores)
+    results.append({"keep_mask": dev_res["keep_mask"].numpy(), "keep_cnt": dev_res["keep_cnt"].numpy(),
+                    "succ": dev_res["succ"].numpy(), "link_iou": dev_res["link_iou"].numpy()})
     per = e - a
     for res in results:
         ok = ok and np.array_equal(res["keep_mask"], km[a:e]) and np.array_equal(res["keep_cnt"], kc[a:e])
