@@ -1,0 +1,71 @@
+"""bench.py's output contract, checked without a GPU: the last committed bench line of the round carries every
+key the driver and the judge read, and the reference arm (which runs on the host cores) prints the same shape."""
+import glob
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+BASE_KEYS = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches"]
+
+
+def _latest_bench():
+    files = [f for f in glob.glob(os.path.join(ROOT, "profiles", "r[0-9]*_bench_v*.json"))]
+    assert files, "no committed bench line under profiles/"
+    files.sort(key=lambda f: (os.path.basename(f).split("_")[0], int(os.path.basename(f).split("_v")[1].split(".")[0])))
+    return json.load(open(files[-1])), files[-1]
+
+
+def test_committed_bench_line_has_the_contract_keys():
+    line, path = _latest_bench()
+    for k in BASE_KEYS + ["roofline", "cpu_baseline", "clocks"]:
+        assert k in line, (k, path)
+    baseline = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+    assert baseline["metric"].startswith(line["metric"].split(" (")[0])            # boxes/sec ...
+    assert line["unit"] == "boxes/s" and line["higher_is_better"] is True and line["scaling"] == "weak"
+    assert line["vs_baseline"] is None and line["data"] == "synthetic" and line["dtype"] == "f32"
+    assert "workload" in line["config"] and "model" not in line["config"]
+    assert line["n_gpus"] == 1 and line["warmup"] >= 3 and line["gpu_launches"] > 0
+    assert abs(line["value"] - 1000 * 300 / (line["ms_per_step"] / 1e3)) / line["value"] < 1e-6
+    r = line["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in r
+    assert r["bound"] in ("hbm", "tensor") and r["unit"] in ("GB/s", "TFLOP/s")
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    c = line["cpu_baseline"]
+    for k in ("value", "unit", "cores", "kind", "sample"):
+        assert k in c
+    assert c["kind"] in ("reference", "port") and c["cores"] == 1
+    e = line["e2e"]
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in e
+    assert e["h2d_bytes_per_step"] == 1000 * 300 * (4 + 30) * 4 and e["d2h_bytes_per_step"] > 0
+    assert e["value"] < line["value"]                                               # host buffers cannot beat resident inputs
+    k = line["clocks"]
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(k)
+    assert not set(k["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_reference_arm_prints_the_same_shape():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1                                                          # exactly one JSON line
+    line = json.loads(lines[0])
+    for k in BASE_KEYS + ["cpu_baseline", "impl"]:
+        assert k in line, k
+    assert line["impl"] == "reference" and line["gpu_launches"] == 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["e2e"]["value"] == line["value"] == line["cpu_baseline"]["value"]
+    assert line["cpu_baseline"]["cores"] == (os.cpu_count() or 1) and line["cpu_baseline"]["kind"] in ("reference", "port")
+    mine, _ = _latest_bench()
+    assert line["metric"] == mine["metric"] and line["unit"] == mine["unit"]
+    # under torchrun only rank 0 runs it: any other rank exits 0 without output
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    other = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                           capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert other.returncode == 0 and other.stdout.strip() == ""
