@@ -92,3 +92,10 @@ def test_per_slot_staging_streams_new_shards(fake):
         VideoPostProcessor(T, N, C, 0.3, n_slots=2, n_stage=3)
     with pytest.raises(ValueError):
         pp.stage(shards[0][0][:-1], shards[0][1][:-1])
+
+
+def test_gpu_test_body_of_the_staged_path_on_the_harness(fake):
+    """The assertions of tests/test_gpu_nms.py::test_video_postprocessor_two_steps_in_flight (eager streams),
+    verbatim, with the launches swapped for the oracle."""
+    import test_gpu_nms
+    test_gpu_nms.test_video_postprocessor_two_steps_in_flight(False)
