@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvdet_b200.so")
+# VDET_B200_LIB: measurement hook -- load a kernel variant built by tools/build_variant.py instead
+LIB_PATH = os.environ.get("VDET_B200_LIB") or os.path.join(_HERE, "libvdet_b200.so")
 
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED = -1, -2, -3, -4

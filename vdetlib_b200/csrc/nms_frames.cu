@@ -20,7 +20,32 @@
 #include "common.cuh"
 #include "warp_sort.cuh"
 
+// Experiments (off in the product build; tools/build_variant.py builds them as separate libraries):
+//   VDET_EXP_PURE_LDS  the rank search reads the sorted keys through NON-volatile asm loads, which the compiler may
+//                      interleave across the elements of a lane (the volatile form keeps them in program order: one
+//                      probe chain at a time).  Ordering after the key stores comes from a data dependence: every
+//                      probe address contains a token that is defined after the __syncwarp().
+#ifndef VDET_EXP_PURE_LDS
+#define VDET_EXP_PURE_LDS 0
+#endif
+
 namespace vdet {
+
+#if VDET_EXP_PURE_LDS
+__device__ __forceinline__ uint32_t order_token() {
+    uint32_t t;
+    asm volatile("mov.u32 %0, 0;" : "=r"(t) : : "memory");
+    return t;
+}
+__device__ __forceinline__ uint32_t lds_u32_search(const uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+#else
+__device__ __forceinline__ uint32_t order_token() { return 0u; }
+__device__ __forceinline__ uint32_t lds_u32_search(const uint32_t addr) { return lds_u32(addr); }
+#endif
 
 constexpr int NMS_THREADS = 256;
 constexpr int NMS_WARPS = NMS_THREADS / 32;
@@ -310,8 +335,42 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 4 : 1)) nms_frames_
                     // Addresses are 32-bit shared-memory BYTE addresses (one LDS with an immediate offset
                     // per probe instead of index arithmetic + scaling).
                     uint32_t rank[NPER];          // byte address of the element's (skewed) sorted slot
-                    const uint32_t so_b = smem_addr_u32(so);
+                    const uint32_t so_b = smem_addr_u32(so) + order_token();
                     const uint32_t acap_b = so_b + 4u * (uint32_t)(cap + (cap >> 5));
+#if VDET_EXP_PURE_LDS
+                    // four probe chains at a time, branch-free inside a group so that they interleave; lanes
+                    // without an element search for the padding key (their result is never stored)
+                    constexpr int GQ = NPER < 4 ? NPER : 4;
+#pragma unroll
+                    for (int g4 = 0; g4 < NPER; g4 += GQ) {
+                        if (g4 * 32 < cap) {                                   // warp-uniform
+                            uint32_t key4[GQ], ap4[GQ];
+#pragma unroll
+                            for (int q = 0; q < GQ; ++q) {
+                                const int e = (g4 + q) * 32 + lane;
+                                key4[q] = e < n ? score_key(e) : 0xffffffffu;
+                                ap4[q] = so_b;
+                            }
+#pragma unroll
+                            for (int step = 16 * NPER; step >= 32; step >>= 1) {
+#pragma unroll
+                                for (int q = 0; q < GQ; ++q) {
+                                    const uint32_t a = ap4[q] + 4u * (uint32_t)(step + (step >> 5) - 2);
+                                    const uint32_t v = lds_u32_search(a < acap_b ? a : so_b);
+                                    if (a < acap_b && v < key4[q]) ap4[q] += 4u * (uint32_t)(step + (step >> 5));
+                                }
+                            }
+#pragma unroll
+                            for (int step = (NPER > 1 ? 16 : 16 * NPER); step > 0; step >>= 1) {
+#pragma unroll
+                                for (int q = 0; q < GQ; ++q)
+                                    if (lds_u32_search(ap4[q] + 4u * (uint32_t)(step - 1)) < key4[q]) ap4[q] += 4u * (uint32_t)step;
+                            }
+#pragma unroll
+                            for (int q = 0; q < GQ; ++q) rank[g4 + q] = ap4[q];
+                        }
+                    }
+#else
 #pragma unroll
                     for (int r = 0; r < NPER; ++r) {
                         const int e = r * 32 + lane;
@@ -321,14 +380,15 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 4 : 1)) nms_frames_
 #pragma unroll
                             for (int step = 16 * NPER; step >= 32; step >>= 1) {
                                 const uint32_t a = ap + 4u * (uint32_t)(step + (step >> 5) - 2);
-                                if (a < acap_b && lds_u32(a) < key) ap += 4u * (uint32_t)(step + (step >> 5));
+                                if (a < acap_b && lds_u32_search(a) < key) ap += 4u * (uint32_t)(step + (step >> 5));
                             }
 #pragma unroll
                             for (int step = (NPER > 1 ? 16 : 16 * NPER); step > 0; step >>= 1)
-                                if (lds_u32(ap + 4u * (uint32_t)(step - 1)) < key) ap += 4u * (uint32_t)step;
+                                if (lds_u32_search(ap + 4u * (uint32_t)(step - 1)) < key) ap += 4u * (uint32_t)step;
                         }
                         rank[r] = ap;
                     }
+#endif
                     __syncwarp();
 #pragma unroll
                     for (int r = 0; r < NPER; ++r) {
