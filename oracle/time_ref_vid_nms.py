@@ -5,7 +5,10 @@ rows of the video for one class -- it visits every pair of rows, also across fra
 class) `nms` loop instead, which is the favourable restatement for the reference; this script measures the real
 thing on slices of config 2 and extrapolates quadratically.  CPU only.
 
-    python tools/ref_vid_nms_cpu.py > profiles/rNN_ref_vid_nms_cpu.json
+    python -m oracle.time_ref_vid_nms > profiles/rNN_ref_vid_nms_cpu.json
+
+TEST INFRASTRUCTURE (lives under oracle/ because only tests/, smoke() and bench.py's CPU legs may execute the
+oracle): it times the reference, never the product.
 """
 import json
 import os
@@ -16,7 +19,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import build_ref, c_oracle          # noqa: E402  (measurement of the reference, not the product)
+from oracle import build_ref, c_oracle          # noqa: E402
 from vdetlib_b200 import synth                  # noqa: E402
 
 N, C = 300, 30
