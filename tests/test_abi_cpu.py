@@ -67,6 +67,11 @@ def test_no_cpu_fallback_in_product():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no CPU fallback", ""), os.path.join(dirpath, f)
+                assert "kernel_double" not in src and "cuda_fake" not in src, os.path.join(dirpath, f)
+    # nor do the tools: only tests/, smoke() and bench.py's CPU legs execute anything under oracle/
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith((".py", ".sh")):
+            assert "oracle" not in open(os.path.join(ROOT, "tools", f)).read(), f
     with pytest.raises(TypeError):
         ops.iou_matrix(torch.zeros(2, 4), torch.zeros(2, 4))
     from vdetlib_b200.utils import cython_nms
