@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define VDET_ABI_VERSION 1
+#define VDET_ABI_VERSION 2
 
 #define VDET_OK                 0
 #define VDET_ERR_INVALID       (-1)   /* bad argument (adapter raises ValueError)            */
@@ -114,6 +114,25 @@ int vdet_nms_frames_f32(const float* boxes, int box_ld,
                         void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * The keep lists of vdet_nms_frames_f32 (FRAME_MAJOR layout) as ONE contiguous array: what
+ * utils/nms.pyx:43-66 returns per problem -- the kept rows in descending score -- for every
+ * (frame, class), in (frame, class) order, plus prefix offsets:
+ *   keep_off [S*C + 1] int32 exclusive prefix of keep_cnt (device; keep_off_mirror: optional second
+ *            destination, e.g. mapped pinned host memory)
+ *   keep_out [sum K] entries of (frame s, class c) at keep_off[s*C + c] ...:
+ *            VDET_KEEP_U16_LOCAL: uint16 index within the frame; VDET_KEEP_I32_ROW: int32 packed row
+ *   keep_bits (optional) [S*C, ceil(max_seg_len/32)] uint32: bit i of block (s,c) = box i of frame s kept
+ * keep_out / keep_off_mirror / keep_bits may be MAPPED PINNED HOST pointers: the kernels write them
+ * across PCIe directly, which takes a data-dependent sum(K) home without a host synchronisation.
+ * ------------------------------------------------------------------------------------- */
+#define VDET_KEEP_U16_LOCAL 0
+#define VDET_KEEP_I32_ROW   1
+int vdet_compact_keep(const int32_t* keep_idx, const int32_t* keep_cnt, const int32_t* seg_offsets,
+                      int n_segs, int max_seg_len, int n_classes, int out_dtype,
+                      int32_t* keep_off, int32_t* keep_off_mirror, void* keep_out,
+                      uint32_t* keep_bits, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Drop-in NMS entry points (SYNCHRONOUS: they return the kept count).
  * Replace utils.cython_nms.nms / vid_nms / track_det_nms (utils/nms.pyx:17,71,128).
  *   dets   [n, ncol] float32 row-major with row stride `ld` floats;
@@ -189,10 +208,15 @@ int vdet_iou_bitmask_f32(const float* boxes, int n, double thresh, uint32_t* mas
  * linked against `halo_boxes` [n_halo,4] (the first frame of the next shard, from the
  * boundary allgather); succ is then halo_row_base + the index into the halo (-1 when n_halo == 0).
  * halo_row_base lets a caller split one video into two calls (frames [0,k) with frame k as the
- * halo and halo_row_base = its packed row offset) and still get packed-row successors.
+ * halo and halo_row_base = its packed row offset) and still get packed-row successors; a shard of
+ * a multi-GPU run passes its own row count, so that halo successors lie BEYOND the local rows
+ * (succ >= n_rows = "continues on the next shard") instead of aliasing them.
+ * n_halo_dev (optional, device): the halo's box count when only the device knows it (ragged
+ * frames: it arrives with the boundary all-gather); n_halo is then the capacity of halo_boxes.
  * ------------------------------------------------------------------------------------- */
 int vdet_link_frames_f32(const float* boxes, const int32_t* seg_offsets, int n_segs,
-                         int max_seg_len, const float* halo_boxes, int n_halo, int halo_row_base,
+                         int max_seg_len, const float* halo_boxes, int n_halo,
+                         const int32_t* n_halo_dev, int halo_row_base,
                          int32_t* succ, float* best_iou, int64_t n_rows, void* stream);
 
 /* ---------------------------------------------------------------------------------------
@@ -260,14 +284,16 @@ int vdet_tubelet_interpolate_f64(const double* knot_x, const double* knot_y, int
 /* ---------------------------------------------------------------------------------------
  * Links -> tubelet score rows (build-defined glue between vdet_link_frames_f32 and the temporal
  * kernels; the reference obtains tubelets from external trackers, vdet/track.py:18-106).
- *   follow_links: chain k starts at packed row start[k] and follows succ[]; it ends at succ == -1
- *                 or when link_iou < min_iou.  chain_rows [n_frames, n_chains] int32 (-1 after the end).
+ *   follow_links: chain k starts at packed row start[k] and follows succ[]; it ends at succ == -1,
+ *                 at succ >= n_rows (the link leaves this shard: halo successors, see
+ *                 vdet_link_frames_f32) or when link_iou < min_iou.
+ *                 chain_rows [n_frames, n_chains] int32 (-1 after the end).
  *   gather_chain_scores: out [n_chains, n_classes, n_frames] float32 = class scores along each chain,
  *                 `missing` (-1e5, utils/protocol.py:459) after its end -- the rows that
  *                 vdet_score_completion / vdet_temporal_maxpool / vdet_temporal_conv1d consume.
  * ------------------------------------------------------------------------------------- */
-int vdet_follow_links(const int32_t* succ, const float* link_iou, const int32_t* start, int n_chains,
-                      int n_frames, float min_iou, int32_t* chain_rows, void* stream);
+int vdet_follow_links(const int32_t* succ, const float* link_iou, int64_t n_rows, const int32_t* start,
+                      int n_chains, int n_frames, float min_iou, int32_t* chain_rows, void* stream);
 int vdet_gather_chain_scores_f32(const float* scores, int n_classes, const int32_t* chain_rows,
                                  int n_chains, int n_frames, float missing, float* out, void* stream);
 

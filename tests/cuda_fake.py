@@ -60,13 +60,13 @@ class FakeLib(object):
     def vdet_nms_frames_f32(self, boxes, box_ld, scores, ldr, ldc, seg, n_segs, max_len, row_ids, C, thresh,
                             keep_idx, keep_cnt, keep_mask, n_rows, layout, status, ws, ws_bytes, stream):
         assert box_ld == 4 and ldc == 1 and ldr == C and row_ids is None and layout == 1     # frame-major
-        off = _view(seg, np.int32, n_segs + 1).copy()
+        off = _view(seg, np.int32, n_segs + 1).copy()           # ABSOLUTE rows: base pointers are the shard's
         n = int(off[-1])
-        assert n == n_rows
+        assert n <= n_rows
         b = _view(boxes, np.float32, n * 4).reshape(n, 4)
         s = _view(scores, np.float32, n * C).reshape(n, C)
         ki = _view(keep_idx, np.int32, n * C)
-        km = _view(keep_mask, np.uint8, n * C)
+        km = _view(keep_mask, np.uint8, n * C) if keep_mask else None
         kc = _view(keep_cnt, np.int32, n_segs * C).reshape(n_segs, C)
         self.nms_calls.append((int(boxes), n_segs))
         for f in range(n_segs):
@@ -74,20 +74,50 @@ class FakeLib(object):
             m = e - a
             for c in range(C):
                 d = np.concatenate([b[a:e], s[a:e, c:c + 1]], axis=1).astype(np.float32)
-                k = np.asarray(c_oracle.nms(d, thresh), dtype=np.int64)
+                try:
+                    k = np.asarray(c_oracle.nms(d, thresh), dtype=np.int64)
+                except ZeroDivisionError:                       # nms.pyx:64 -> the device status word
+                    _view(status, np.uint32, 1)[0] |= 1
+                    k = np.zeros(0, np.int64)
                 blk = a * C + c * m
                 ki[blk:blk + m] = -1
                 ki[blk:blk + len(k)] = a + k
-                km[blk:blk + m] = 0
-                km[blk + k] = 1
+                if km is not None:
+                    km[blk:blk + m] = 0
+                    km[blk + k] = 1
                 kc[f, c] = len(k)
+        return 0
+
+    def vdet_compact_keep(self, keep_idx, keep_cnt, seg, n_segs, max_seg_len, C, out_dtype, keep_off, keep_off_mirror,
+                          keep_out, keep_bits, stream):
+        """include/vdet_b200.h: padded frame-major blocks -> one contiguous list + prefix offsets (+ bit masks)."""
+        off = _view(seg, np.int32, n_segs + 1)
+        cnt = _view(keep_cnt, np.int32, n_segs * C)
+        pre = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+        for dst in (keep_off, keep_off_mirror):
+            if dst:
+                _view(dst, np.int32, n_segs * C + 1)[:] = pre
+        ki = _view(keep_idx, np.int32, int(off[-1]) * C)
+        out = _view(keep_out, np.uint16 if out_dtype == 0 else np.int32, max(int(pre[-1]), 1))
+        words = (max_seg_len + 31) // 32
+        bits = _view(keep_bits, np.uint32, n_segs * C * words).reshape(n_segs * C, words) if keep_bits else None
+        for f in range(n_segs):
+            a, m = int(off[f]), int(off[f + 1] - off[f])
+            for c in range(C):
+                k = f * C + c
+                rows = ki[a * C + c * m:a * C + c * m + cnt[k]]
+                out[pre[k]:pre[k + 1]] = (rows - a) if out_dtype == 0 else rows
+                if bits is not None:
+                    bits[k] = 0
+                    for loc in rows - a:
+                        bits[k, loc >> 5] |= np.uint32(1 << (loc & 31))
         return 0
 
     def vdet_last_error(self):
         return b""
 
 
-def link_frames(boxes, seg_offsets, max_seg_len, halo=None, halo_row_base=0, out=None):
+def link_frames(boxes, seg_offsets, max_seg_len, halo=None, halo_row_base=0, out=None, halo_count=None):
     """ops.link_frames on CPU tensors: FIRST arg-max IoU box of the next frame (halo for the last frame)."""
     b, off = boxes.numpy(), seg_offsets.numpy()
     n = b.shape[0]
@@ -100,13 +130,15 @@ def link_frames(boxes, seg_offsets, max_seg_len, halo=None, halo_row_base=0, out
             nxt, base = b[off[f + 1]:off[f + 2]], int(off[f + 1])
         else:
             nxt, base = (halo.numpy() if halo is not None else np.zeros((0, 4), np.float32)), int(halo_row_base)
+            if halo_count is not None:
+                nxt = nxt[:max(0, min(int(halo_count.numpy().ravel()[0]), len(nxt)))]
         if e > a and len(nxt):
             iou = c_oracle.pair_iou_f32(b[a:e], nxt)
             succ[a:e] = base + np.argmax(iou, axis=1)
             best[a:e] = iou.max(axis=1)
     if out is not None:
-        out[0].copy_(torch.from_numpy(succ))
-        out[1].copy_(torch.from_numpy(best))
+        out[0][:n].copy_(torch.from_numpy(succ))
+        out[1][:n].copy_(torch.from_numpy(best))
         return out
     return torch.from_numpy(succ), torch.from_numpy(best)
 

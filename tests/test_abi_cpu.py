@@ -34,7 +34,7 @@ def test_library_exports_every_symbol(lib_path):
     for name in _header_functions():
         assert hasattr(lib, name), name
     lib.vdet_abi_version.restype = ctypes.c_int
-    assert lib.vdet_abi_version() == 1
+    assert lib.vdet_abi_version() == 2
     lib.vdet_last_error.restype = ctypes.c_char_p
     assert isinstance(lib.vdet_last_error(), bytes)
 

@@ -43,16 +43,16 @@ def _worker(rank, world, port, out_dir):
     frames = [rng.uniform(0, 100, (c, 4)).astype(np.float32) for c in counts]
     a, b = shard_range(len(frames), world, rank)
     ex = BoundaryExchange(max_boxes=8, device="cpu")
-    h = ex.start(torch.from_numpy(frames[a]))
-    halo = ex.finish(h)
-    if rank == world - 1:
-        ok = halo is None
-    else:
-        ok = halo is not None and np.array_equal(halo.numpy(), frames[b])
-    # uniform-count fast path (no count read-back)
-    h = ex.start(torch.from_numpy(frames[a]))
-    halo2 = ex.finish(h, count_hint=None if rank == world - 1 else counts[b])
-    ok = ok and (halo2 is None if rank == world - 1 else np.array_equal(halo2.numpy(), frames[b]))
+    ok = True
+    for _ in range(2):                     # second round: the count word is only rewritten when it changes
+        h = ex.start(torch.from_numpy(frames[a]))
+        halo, halo_count = ex.finish(h)
+        if rank == world - 1:
+            ok = ok and halo is None and halo_count is None
+        else:
+            # a fixed-capacity buffer + the neighbour's count as an int32 device word (no host read-back needed)
+            ok = ok and halo.shape == (8, 4) and halo_count.dtype == torch.int32 and int(halo_count[0]) == counts[b]
+            ok = ok and np.array_equal(halo.numpy()[:counts[b]], frames[b])
     with open(os.path.join(out_dir, "rank%d" % rank), "w") as f:
         f.write("ok" if ok else "bad")
     dist.barrier()
@@ -188,23 +188,30 @@ def _sharded_pipeline_worker(rank, world, port, out_dir):
     mpatch = pytest.MonkeyPatch()
     cuda_fake.install(mpatch)                                      # fake streams, oracle-backed launches, CPU tensors
     from vdetlib_b200.dist import ShardedVideoPostProcessor, shard_range
-    T, N, C, thr = 4 * world, 40, 3, 0.3                          # equal shards (the processor has a fixed shape)
+    T, N, C, thr = 4 * world, 40, 3, 0.3
     b, s = synth.boxes_scores(T, N, C, seed=12)
     km, _, kc = c_oracle.nms_frames(b, s, thr)
     ls, lb = c_oracle.link_f32(b)                                  # [T-1, N]: successor index inside frame t+1
     a, e = shard_range(T, world, rank)
-    pp = ShardedVideoPostProcessor(e - a, N, C, thr, torch.device("cpu"))
-    pp.pp.stage(b[a:e], s[a:e])
+    per = e - a
+    pp = ShardedVideoPostProcessor(per, N, C, thr, torch.device("cpu"))
     ok = True
-    # two steps in flight through the boundary exchange, then a synchronous step
-    tickets = [pp.submit_host(), pp.submit_host()]
-    results = [{k: np.array(v, copy=True) for k, v in pp.collect(t).items()} for t in tickets]
-    results.append(pp.step_host())
+    # two NEW-shard steps in flight through the boundary exchange (per-slot staging), a re-submission of the staged
+    # shard, then a synchronous step
+    tickets = [pp.submit_host(b[a:e], s[a:e], graph=False), pp.submit_host(b[a:e], s[a:e], graph=False)]
+    results = []
+    for t in tickets:
+        r = pp.collect(t)
+        results.append({"keep_mask": r.keep_mask(), "keep_cnt": np.array(r["keep_cnt"]), "succ": np.array(r["succ"]),
+                        "link_iou": np.array(r["link_iou"])})
+    r = pp.collect(pp.submit_staged(graph=False))
+    results.append({"keep_mask": r.keep_mask(), "keep_cnt": r["keep_cnt"], "succ": r["succ"], "link_iou": r["link_iou"]})
+    r = pp.step_host(b[a:e], s[a:e])
+    results.append({"keep_mask": r.keep_mask(), "keep_cnt": r["keep_cnt"], "succ": r["succ"], "link_iou": r["link_iou"]})
     # the device-resident step (exchange beside the NMS, then the link) on the staged shard
     dev_res = pp.step_device(pp.pp.d_boxes, pp.pp.d_scores)
     results.append({"keep_mask": dev_res["keep_mask"].numpy(), "keep_cnt": dev_res["keep_cnt"].numpy(),
                     "succ": dev_res["succ"].numpy(), "link_iou": dev_res["link_iou"].numpy()})
-    per = e - a
     for res in results:
         ok = ok and np.array_equal(res["keep_mask"], km[a:e]) and np.array_equal(res["keep_cnt"], kc[a:e])
         succ = res["succ"].reshape(per, N)
@@ -212,11 +219,38 @@ def _sharded_pipeline_worker(rank, world, port, out_dir):
         for t in range(per):
             g = a + t                                              # global frame
             if g < T - 1:
-                # inside the shard: packed local row of frame t+1; across the boundary: index into the halo
-                base = (t + 1) * N if t < per - 1 else 0
+                # inside the shard: packed local row of frame t+1; across the boundary: rows + index into the
+                # neighbour's first frame, i.e. BEYOND the local rows (never aliasing them)
+                base = (t + 1) * N
                 ok = ok and np.array_equal(succ[t] - base, ls[g]) and np.array_equal(iou[t], lb[g])
             else:
                 ok = ok and np.all(succ[t] == -1)
+    # ragged shards: every rank a different number of frames and boxes; the neighbour's first-frame count is
+    # only known through the exchange (device word), chains end at the shard boundary
+    rng = np.random.default_rng(5)
+    counts_all = [rng.integers(0, N + 1, 3 + r).astype(np.int32) for r in range(world)]
+    for c in counts_all:
+        c[0] = max(int(c[0]), 1)
+    frames_all = [[synth.boxes_scores(1, N, C, seed=100 * r + f) for f in range(len(counts_all[r]))] for r in range(world)]
+    cnt = counts_all[rank]
+    fb = [frames_all[rank][f][0][0, :cnt[f]] for f in range(len(cnt))]
+    fs = [frames_all[rank][f][1][0, :cnt[f]] for f in range(len(cnt))]
+    pp2 = ShardedVideoPostProcessor(3 + world, N, C, thr, torch.device("cpu"), n_chunks=2)
+    r = pp2.collect(pp2.submit_host(np.concatenate(fb), np.concatenate(fs), counts=cnt, graph=False))
+    rows = int(cnt.sum())
+    last_a = rows - int(cnt[-1])
+    if cnt[-1] > 0:
+        if rank < world - 1:
+            nxt = frames_all[rank + 1][0][0][0, :counts_all[rank + 1][0]]
+            iou = c_oracle.pair_iou_f32(fb[-1], nxt)
+            ok = ok and np.array_equal(r["succ"][last_a:], rows + np.argmax(iou, axis=1))
+            ok = ok and np.array_equal(r["link_iou"][last_a:], iou.max(axis=1))
+        else:
+            ok = ok and np.all(r["succ"][last_a:] == -1)
+    for f in range(len(cnt)):
+        for c in range(C):
+            d = np.concatenate([fb[f], fs[f][:, c:c + 1]], axis=1).astype(np.float32)
+            ok = ok and np.array_equal(r.keep_list(f, c), np.asarray(c_oracle.nms(d, thr), dtype=np.int64))
     with open(os.path.join(out_dir, "rank%d" % rank), "w") as f:
         f.write("ok" if ok else "bad")
     mpatch.undo()

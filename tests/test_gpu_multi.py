@@ -38,13 +38,16 @@ def test_virtual_shards_single_gpu():
         sb = torch.from_numpy(b[k * per:(k + 1) * per].reshape(-1, 4)).to(dev)
         seg = ops.seg_offsets_uniform(per, N, dev)
         halo = torch.from_numpy(b[(k + 1) * per]).to(dev) if k < S - 1 else None
-        su, io = ops.link_frames(sb, seg, N, halo)
-        su = su.cpu().numpy().astype(np.int64)
+        su, io = ops.link_frames(sb, seg, N, halo, halo_row_base=per * N)
         want = succ[k * per * N:(k + 1) * per * N].astype(np.int64)
-        # inside the shard successors are shard-local rows; across the boundary they index the halo
+        # inside the shard successors are shard-local rows; across the boundary they are rows + halo index,
+        # i.e. the global successor minus the shard's first row again -- one formula for both
         local = np.where(want >= 0, want - k * per * N, -1)
-        local[(per - 1) * N:] = np.where(want[(per - 1) * N:] >= 0, want[(per - 1) * N:] - (k + 1) * per * N, -1)
-        assert np.array_equal(su, local)
+        assert np.array_equal(su.cpu().numpy().astype(np.int64), local)
+        # chains followed on the shard end at the boundary instead of wrapping into the shard's first frame
+        start = torch.arange((per - 2) * N, (per - 2) * N + 8, dtype=torch.int32, device=dev)
+        rows = ops.follow_links(su, io, start, 3).cpu().numpy()
+        assert np.array_equal(rows[1], local[(per - 2) * N:(per - 2) * N + 8]) and np.all(rows[2] == -1)
         assert np.array_equal(io.cpu().numpy(), iou[k * per * N:(k + 1) * per * N])
 
 
@@ -60,21 +63,23 @@ def _worker(rank, world, port, T, N, C, thr, out_dir):
     b, s = synth.boxes_scores(T, N, C, seed=12)
     a, e = shard_range(T, world, rank)
     pp = ShardedVideoPostProcessor(e - a, N, C, thr, dev)
-    pp.pp.stage(b[a:e], s[a:e])
-    res = pp.step_host()
-    # the device-resident step (what bench.py's `value` times) on the same shard: local link first,
-    # boundary link last -- must give the same arrays as the staged step
+    res = pp.step_host(b[a:e], s[a:e])
+    res = {"keep_mask": res.keep_mask(), "keep_cnt": np.array(res["keep_cnt"]), "succ": np.array(res["succ"]),
+           "link_iou": np.array(res["link_iou"]), "keep_idx": np.array(res["keep_idx"]), "keep_off": np.array(res["keep_off"])}
+    # the device-resident step (what bench.py's `value` times) on the same shard must give the same arrays
     dev_res = pp.step_device(pp.pp.d_boxes, pp.pp.d_scores)
     torch.cuda.synchronize()
     for key in ("keep_mask", "keep_cnt", "succ", "link_iou"):
-        assert np.array_equal(dev_res[key].cpu().numpy().reshape(np.asarray(res[key]).shape), np.asarray(res[key])), key
-    # two steps in flight through the boundary exchange
-    t0 = pp.submit_host()
-    t1 = pp.submit_host()
-    r0 = {k: np.array(v, copy=True) for k, v in pp.collect(t0).items()}
-    r1 = pp.collect(t1)
-    for key in ("keep_mask", "keep_cnt", "succ", "link_iou"):
-        assert np.array_equal(r0[key], np.asarray(res[key])) and np.array_equal(np.asarray(r1[key]), np.asarray(res[key])), key
+        assert np.array_equal(dev_res[key].cpu().numpy().reshape(res[key].shape), res[key]), key
+    # two steps in flight through the boundary exchange: new shards from pageable memory, eager and graph replay
+    for graph in (False, True):
+        t0 = pp.submit_host(b[a:e], s[a:e], graph=graph)
+        t1 = pp.submit_host(b[a:e].copy(), s[a:e].copy(), graph=graph)
+        r0 = pp.collect(t0)
+        r0 = {k: np.array(r0[k], copy=True) for k in ("keep_idx", "keep_off", "succ", "link_iou")}
+        r1 = pp.collect(t1)
+        for key in ("keep_idx", "keep_off", "succ", "link_iou"):
+            assert np.array_equal(r0[key], res[key]) and np.array_equal(np.asarray(r1[key]), res[key]), (key, graph)
     # frame-sharded vid_nms of one class with the global keep-order merge
     from vdetlib_b200.dist import sharded_vid_nms
     s_glob = s[:, :, 0] + np.arange(T)[:, None] * 1e-5                      # unique across the video
@@ -113,7 +118,5 @@ def test_sharded_pipeline_matches_single_gpu(tmp_path, world):
         assert np.array_equal(got["keep_mask"], mask[:, lo:hi].reshape(C, per, N).transpose(1, 0, 2))
         assert np.array_equal(got["link_iou"], iou[lo:hi])
         want = succ[lo:hi].astype(np.int64)
-        local = np.where(want >= 0, want - lo, -1)
-        if r < world - 1:
-            local[(per - 1) * N:] = np.where(want[(per - 1) * N:] >= 0, want[(per - 1) * N:] - hi, -1)
+        local = np.where(want >= 0, want - lo, -1)          # boundary successors: rows + halo index == global - lo
         assert np.array_equal(got["succ"].astype(np.int64), local)

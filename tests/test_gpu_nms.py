@@ -278,7 +278,10 @@ def test_frame_major_layout_and_pipelined_postprocessor():
     for n_chunks in (1, 3, 10):
         pp = VideoPostProcessor(T2, N2, C2, 0.3, n_chunks=n_chunks)
         out = pp.run_host(b2, s2)
-        assert np.array_equal(out["keep_mask"], km2) and np.array_equal(out["keep_cnt"], kc2)
+        assert np.array_equal(out.keep_mask(), km2) and np.array_equal(out["keep_cnt"], kc2)
+        for t in range(T2):                                          # ordered keep lists, frame-local indices
+            for c in range(C2):
+                assert np.array_equal(out.keep_list(t, c), ki2[t, c, :kc2[t, c]]), (t, c)
         got = out["succ"][:(T2 - 1) * N2].reshape(T2 - 1, N2) - np.arange(1, T2)[:, None] * N2
         assert np.array_equal(got, ls) and np.array_equal(out["link_iou"][:(T2 - 1) * N2].reshape(T2 - 1, N2), lb)
         dev_out = pp.run_device(pp.d_boxes, pp.d_scores)
@@ -296,7 +299,7 @@ def test_video_postprocessor_two_steps_in_flight(graph):
     eager stream pipeline and whole-step CUDA-graph replay -- same results as the oracle every time."""
     from vdetlib_b200.vdet.video_det import VideoPostProcessor
     T, N, C = 12, 150, 7
-    pp = VideoPostProcessor(T, N, C, 0.3, n_chunks=4)
+    pp = VideoPostProcessor(T, N, C, 0.3, n_chunks=4, n_stage=1)
     data = [synth.boxes_scores(T, N, C, seed=300 + k) for k in range(3)]
     want = []
     for b, s in data:
@@ -306,7 +309,7 @@ def test_video_postprocessor_two_steps_in_flight(graph):
 
     def check(out, w):
         km, kc, ls, lb = w
-        assert np.array_equal(out["keep_mask"], km) and np.array_equal(out["keep_cnt"], kc)
+        assert np.array_equal(out.keep_mask(), km) and np.array_equal(out["keep_cnt"], kc)
         got = out["succ"][:(T - 1) * N].reshape(T - 1, N) - np.arange(1, T)[:, None] * N
         assert np.array_equal(got, ls)
         assert np.array_equal(out["link_iou"][:(T - 1) * N].reshape(T - 1, N), lb)
@@ -332,6 +335,118 @@ def test_video_postprocessor_two_steps_in_flight(graph):
     check(out, want[0])
     dev_out = pp.run_device(pp.d_boxes, pp.d_scores)
     assert np.array_equal(dev_out["keep_mask"].cpu().numpy(), want[0][0])
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_video_postprocessor_streams_new_shards_from_pageable_memory(graph):
+    """submit_host / collect with a NEW shard per step from ordinary (pageable) NumPy arrays, two steps in
+    flight on per-slot staging buffers: every ticket returns the ordered keep lists and the link of ITS shard;
+    a status flag raised by one shard does not poison the next one."""
+    from vdetlib_b200.vdet.video_det import VideoPostProcessor
+    T, N, C = 10, 200, 5
+    pp = VideoPostProcessor(T, N, C, 0.3, n_chunks=3, want_bits=True)
+    shards = [synth.boxes_scores(T, N, C, seed=900 + k) for k in range(5)]
+
+    def check(out, b, s):
+        km, ki, kc = c_oracle.nms_frames(b, s, 0.3)
+        ls, lb = c_oracle.link_f32(b)
+        assert np.array_equal(out["keep_cnt"], kc) and np.array_equal(out.keep_mask(), km)
+        for t in range(T):
+            for c in range(C):
+                assert np.array_equal(out.keep_list(t, c), ki[t, c, :kc[t, c]]), (t, c)
+        bits = np.unpackbits(out["keep_bits"].view(np.uint8), bitorder="little").reshape(T, C, -1)[:, :, :N]
+        assert np.array_equal(bits, km)
+        got = out["succ"][:(T - 1) * N].reshape(T - 1, N) - np.arange(1, T)[:, None] * N
+        assert np.array_equal(got, ls) and np.all(out["succ"][(T - 1) * N:] == -1)
+        assert np.array_equal(out["link_iou"][:(T - 1) * N].reshape(T - 1, N), lb)
+
+    tickets = [pp.submit_host(*shards[0], graph=graph)]
+    for k in range(1, len(shards)):
+        tickets.append(pp.submit_host(*shards[k], graph=graph))
+        check(pp.collect(tickets[k - 1]), *shards[k - 1])
+    check(pp.collect(tickets[-1]), *shards[-1])
+    # a degenerate shard raises ZeroDivisionError (nms.pyx:64) ...
+    bad_b, bad_s = shards[0][0].copy(), shards[0][1].copy()
+    bad_b[3, :2] = np.asarray([10.0, 10.0, 9.0, 20.0], np.float32)          # two boxes of width 0: union == 0
+    bad_s[3, 0, :], bad_s[3, 1, :] = 0.9995, 0.9994
+    with pytest.raises(ZeroDivisionError):
+        pp.collect(pp.submit_host(bad_b, bad_s, graph=graph))
+    # ... and the next clean shard on the same slot is clean again (ADVICE r01: status word reset per step)
+    for k in range(2):
+        check(pp.collect(pp.submit_host(*shards[k], graph=graph)), *shards[k])
+
+
+def test_video_postprocessor_ragged_frames():
+    """Ragged shards (packed rows + counts) through the staged pipeline, chunk edges balanced by rows."""
+    from vdetlib_b200.vdet.video_det import VideoPostProcessor
+    N, C = 300, 6
+    pp = VideoPostProcessor(12, N, C, 0.3, n_chunks=4)
+    for trial, counts in enumerate([[5, 0, 64, 300, 33, 1, 128, 7], [300] * 12, [0, 0, 9], [17]]):
+        counts = np.asarray(counts, np.int32)
+        T = len(counts)
+        b, s = synth.boxes_scores(T, N, C, seed=950 + trial)
+        km, ki, kc = c_oracle.nms_frames(b, s, 0.3, counts)
+        rows_b = np.concatenate([b[t, :counts[t]] for t in range(T)])
+        rows_s = np.concatenate([s[t, :counts[t]] for t in range(T)])
+        off = np.concatenate([[0], np.cumsum(counts)])
+        out = pp.collect(pp.submit_host(rows_b, rows_s, counts=counts))
+        assert np.array_equal(out["keep_cnt"], kc)
+        for t in range(T):
+            for c in range(C):
+                assert np.array_equal(out.keep_list(t, c), ki[t, c, :kc[t, c]]), (trial, t, c)
+        for t in range(T):
+            a, e = off[t], off[t + 1]
+            if e == a:
+                continue
+            if t + 1 < T and counts[t + 1] > 0:
+                iou = c_oracle.pair_iou_f32(b[t, :counts[t]], b[t + 1, :counts[t + 1]])
+                assert np.array_equal(out["succ"][a:e], off[t + 1] + np.argmax(iou, axis=1))
+                assert np.array_equal(out["link_iou"][a:e], iou.max(axis=1))
+            else:
+                assert np.all(out["succ"][a:e] == -1)
+
+
+def test_compact_keep_matches_padded_blocks():
+    """vdet_compact_keep: the padded frame-major keep blocks as one contiguous list (uint16 local / int32 row),
+    prefix offsets and bit masks -- including a big-frame shard (2000-box frames)."""
+    from vdetlib_b200 import _lib
+    dev = torch.device("cuda")
+    lib = _lib.load()
+    for counts, C in (([300] * 7, 30), ([5, 0, 64, 300, 33, 1, 128, 7], 4), ([2000, 1500, 3], 3)):
+        counts = np.asarray(counts, np.int32)
+        T, nmax = len(counts), int(counts.max())
+        b, s = synth.boxes_scores(T, nmax, C, seed=960)
+        rows_b = np.concatenate([b[t, :counts[t]] for t in range(T)])
+        rows_s = np.concatenate([s[t, :counts[t]] for t in range(T)])
+        off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+        d_off = torch.from_numpy(off).to(dev)
+        keep_idx, keep_cnt, _, status = ops.nms_frames(torch.from_numpy(rows_b).to(dev), torch.from_numpy(rows_s).to(dev),
+                                                       d_off, 0.3, nmax, frame_major_out=True)
+        gi, gc = keep_idx.cpu().numpy(), keep_cnt.cpu().numpy()
+        nb, W = T * C, (nmax + 31) // 32
+        for dtype, tdt in ((_lib.KEEP_U16_LOCAL, torch.uint16), (_lib.KEEP_I32_ROW, torch.int32)):
+            k_off = torch.empty(nb + 1, dtype=torch.int32, device=dev)
+            k_off2 = torch.zeros(nb + 1, dtype=torch.int32).pin_memory()
+            k_out = torch.zeros(int(gc.sum()) + 8, dtype=tdt).pin_memory()      # mapped pinned host memory
+            k_bits = torch.empty((nb, W), dtype=torch.int32, device=dev)
+            _lib.check(lib.vdet_compact_keep(keep_idx.data_ptr(), keep_cnt.data_ptr(), d_off.data_ptr(), T, nmax, C, dtype,
+                                             k_off.data_ptr(), k_off2.data_ptr(), k_out.data_ptr(), k_bits.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream), "compact_keep")
+            torch.cuda.synchronize()
+            pre = np.concatenate([[0], np.cumsum(gc.reshape(-1))])
+            assert np.array_equal(k_off.cpu().numpy(), pre) and np.array_equal(k_off2.numpy(), pre)
+            got, bits = k_out.numpy(), k_bits.cpu().numpy().view(np.uint32)
+            for t in range(T):
+                n = counts[t]
+                for c in range(C):
+                    k = t * C + c
+                    rows = gi[off[t] * C + c * n:off[t] * C + c * n + gc[t, c]]
+                    want = rows - off[t] if dtype == _lib.KEEP_U16_LOCAL else rows
+                    assert np.array_equal(got[pre[k]:pre[k + 1]].astype(np.int64), want), (t, c)
+                    m = np.zeros(W * 32, np.uint8)
+                    m[rows - off[t]] = 1
+                    assert np.array_equal(np.unpackbits(bits[k].view(np.uint8), bitorder="little"), m), (t, c)
+            assert np.all(got[pre[-1]:] == 0)                                   # nothing written beyond sum K
 
 
 def test_sort_by_score_desc():

@@ -18,6 +18,7 @@ DTYPE_F32, DTYPE_F64 = 0, 1
 POOL_ARGMAX_SCORE, POOL_ARGMAX_IOU, POOL_MAX_IOU = 0, 1, 2
 PAD_ZERO, PAD_EDGE = 0, 1
 LAYOUT_CLASS_MAJOR, LAYOUT_FRAME_MAJOR = 0, 1
+KEEP_U16_LOCAL, KEEP_I32_ROW = 0, 1
 
 _c = ctypes
 _vp, _i32, _i64, _f64, _f32, _sz = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_double, _c.c_float, _c.c_size_t
@@ -33,6 +34,7 @@ SIGNATURES = {
     "vdet_nms_frames_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "vdet_nms_frames_f32": (_i32, [_vp, _i32, _vp, _i64, _i64, _vp, _i32, _i32, _vp, _i32, _f64,
                                    _vp, _vp, _vp, _i64, _i32, _vp, _vp, _sz, _vp]),
+    "vdet_compact_keep": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "vdet_nms_workspace_bytes": (_sz, [_i64, _i32]),
     "vdet_nms_f32": (_i64, [_vp, _i64, _i32, _f64, _vp, _vp, _vp, _sz, _vp]),
     "vdet_vid_nms_f32": (_i64, [_vp, _i64, _i32, _f64, _vp, _vp, _vp, _sz, _vp]),
@@ -43,7 +45,7 @@ SIGNATURES = {
     "vdet_iou_matrix_f32": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "vdet_iou_matrix_f64": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "vdet_iou_bitmask_f32": (_i32, [_vp, _i32, _f64, _vp, _vp, _vp]),
-    "vdet_link_frames_f32": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _i64, _vp]),
+    "vdet_link_frames_f32": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _i64, _vp]),
     "vdet_spatial_maxpool": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _i64, _i32, _vp, _i32, _f64, _i32,
                                     _vp, _vp, _vp]),
     "vdet_score_completion_workspace_bytes": (_sz, [_i64, _i64, _i32]),
@@ -51,7 +53,7 @@ SIGNATURES = {
     "vdet_temporal_maxpool": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _i32, _f64, _vp]),
     "vdet_temporal_conv1d": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _vp]),
     "vdet_tubelet_interpolate_f64": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp]),
-    "vdet_follow_links": (_i32, [_vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp]),
+    "vdet_follow_links": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _f32, _vp, _vp]),
     "vdet_gather_chain_scores_f32": (_i32, [_vp, _i32, _vp, _i32, _i32, _f32, _vp, _vp]),
     "vdet_sort_workspace_bytes": (_sz, [_i64]),
     "vdet_sort_by_score_desc": (_i32, [_vp, _i32, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
@@ -78,7 +80,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the header and the library diverge
         fn.restype = res
         fn.argtypes = args
-    if lib.vdet_abi_version() != 1:
+    if lib.vdet_abi_version() != 2:
         raise RuntimeError("vdetlib_b200: ABI version mismatch")
     _lib = lib
     return lib

@@ -3,7 +3,8 @@
 // tubelets from external trackers, vdet/track.py:18-106).
 //
 //   follow_links : chain k starts at packed row start[k] and follows succ[] frame by frame; a chain
-//                  ends at succ == -1 or when the link IoU drops below min_iou.  One thread per
+//                  ends at succ == -1, at succ >= n_rows (a halo successor: the chain continues on
+//                  the next shard, include/vdet_b200.h) or when the link IoU drops below min_iou.  One thread per
 //                  chain (pointer chasing is inherently serial along the frame axis; chains run in
 //                  parallel), rows written frame-major so that the T stores of a warp's 32 chains
 //                  coalesce.
@@ -14,18 +15,19 @@
 namespace vdet {
 
 __global__ void __launch_bounds__(128) follow_links_kernel(const int32_t* __restrict__ succ,
-                                                           const float* __restrict__ link_iou,
+                                                           const float* __restrict__ link_iou, int64_t n_rows,
                                                            const int32_t* __restrict__ start, int n_chains,
                                                            int n_frames, float min_iou,
                                                            int32_t* __restrict__ chain_rows) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_chains) return;
     int row = start[k];
+    if (row >= n_rows) row = -1;
     for (int t = 0; t < n_frames; ++t) {
         chain_rows[(int64_t)t * n_chains + k] = row;
         if (row >= 0) {
             const int nxt = __ldg(succ + row);
-            row = (nxt >= 0 && __ldg(link_iou + row) >= min_iou) ? nxt : -1;
+            row = (nxt >= 0 && nxt < n_rows && __ldg(link_iou + row) >= min_iou) ? nxt : -1;
         }
     }
 }
@@ -52,12 +54,12 @@ __global__ void __launch_bounds__(256) gather_chain_scores_kernel(const float* _
 
 using namespace vdet;
 
-extern "C" int vdet_follow_links(const int32_t* succ, const float* link_iou, const int32_t* start, int n_chains,
-                                 int n_frames, float min_iou, int32_t* chain_rows, void* stream) {
-    VDET_REQUIRE(n_chains >= 0 && n_frames >= 0, "follow_links: negative size");
+extern "C" int vdet_follow_links(const int32_t* succ, const float* link_iou, int64_t n_rows, const int32_t* start,
+                                 int n_chains, int n_frames, float min_iou, int32_t* chain_rows, void* stream) {
+    VDET_REQUIRE(n_chains >= 0 && n_frames >= 0 && n_rows >= 0, "follow_links: negative size");
     if (n_chains == 0 || n_frames == 0) return VDET_OK;
     follow_links_kernel<<<(unsigned)((n_chains + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-        succ, link_iou, start, n_chains, n_frames, min_iou, chain_rows);
+        succ, link_iou, n_rows, start, n_chains, n_frames, min_iou, chain_rows);
     VDET_LAUNCH_CHECK();
     return VDET_OK;
 }

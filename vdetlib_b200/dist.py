@@ -21,8 +21,27 @@ def shard_range(n_frames, world_size, rank):
     return start, start + base + (1 if rank < rem else 0)
 
 
+def bind_rank_cpus(local_rank, local_world):
+    """Pin this process to its own slice of the visible CPUs (call BEFORE allocating pinned buffers, so that
+    their pages are first touched from that slice).  On a multi-socket host this keeps a rank's staging
+    copies and the DMA reads of its GPU on the local memory node; on a single-node VM it only stops the
+    ranks' staging threads from migrating over each other.  Returns the CPU list."""
+    import os
+    cpus = sorted(os.sched_getaffinity(0))
+    per = len(cpus) // max(int(local_world), 1)
+    if per < 1:
+        return cpus
+    mine = cpus[local_rank * per:(local_rank + 1) * per]
+    os.sched_setaffinity(0, mine)
+    return mine
+
+
 class BoundaryExchange(object):
-    """All-gather of first-frame boxes; each rank reads its right neighbour's slot."""
+    """All-gather of first-frame boxes; each rank reads its right neighbour's slot.
+
+    Slot layout per rank: [max_boxes, 4] float32 boxes, then one row whose first word holds the box count as
+    int32 BITS -- the link kernel reads the neighbour's count from the device (``halo_count``), so ragged
+    shards need no host round trip.  Buffers have fixed addresses: a CUDA graph can hold them."""
 
     def __init__(self, max_boxes, device, group=None):
         self.group = group
@@ -30,51 +49,61 @@ class BoundaryExchange(object):
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.max_boxes = int(max_boxes)
         self.device = torch.device(device)
-        # slot layout per rank: [max_boxes, 4] boxes then one row holding the count in [0,0]
         self.send = torch.zeros((self.max_boxes + 1, 4), dtype=torch.float32, device=self.device)
         self.recv = torch.zeros((self.world, self.max_boxes + 1, 4), dtype=torch.float32, device=self.device)
+        self._send_count = self.send.view(torch.int32)[self.max_boxes, 0]
         self._sent_count = -1
 
     def start(self, first_frame_boxes):
-        """Enqueue the all-gather (async when the backend supports it); returns a handle."""
+        """Enqueue the all-gather (async when the backend supports it); returns a handle.  ``first_frame_boxes``
+        may be a device tensor or a pinned host tensor (it is copied into the send slot either way)."""
         n = int(first_frame_boxes.shape[0])
         if n > self.max_boxes:
             raise ValueError("first frame has %d boxes > max_boxes %d" % (n, self.max_boxes))
-        self.send[:n].copy_(first_frame_boxes)
+        if n:
+            self.send[:n].copy_(first_frame_boxes, non_blocking=True)
         if n != self._sent_count:
-            # fill_ passes the value as a kernel argument.  (``send[i, 0] = float(n)`` copies a host
-            # scalar from pageable memory: that copy is stream-ordered behind the previous step's
-            # kernels and BLOCKS the host until they finish -- measured: host enqueue time == device
-            # time per step, 0.53 ms instead of 0.46, profiles/r01_multi_probe.json.)
-            self.send[self.max_boxes, 0].fill_(float(n))
+            # fill_ passes the value as a kernel argument.  (``send[i, 0] = n`` copies a host scalar from
+            # pageable memory: that copy is stream-ordered behind the previous step's kernels and BLOCKS
+            # the host until they finish -- measured: host enqueue time == device time per step, 0.53 ms
+            # instead of 0.46, profiles/r01_multi_probe.json.)
+            self._send_count.fill_(n)
             self._sent_count = n
         if self.world == 1:
             return None
         return dist.all_gather_into_tensor(self.recv.view(-1, 4), self.send, group=self.group, async_op=True)
 
-    def finish(self, handle, count_hint=None):
-        """Wait and return the halo = boxes of the next rank's first frame (None on the last rank).
-
-        ``count_hint``: the neighbour's box count when it is known a priori (uniform frames);
-        avoids reading the count back from the device."""
+    def finish(self, handle):
+        """Wait and return (halo, halo_count): the next rank's first-frame buffer [max_boxes, 4] and its box
+        count as an int32 device tensor [1]; (None, None) on the last rank."""
+        if handle is not None:
+            handle.wait()
         if self.world == 1 or self.rank == self.world - 1:
-            if handle is not None:
-                handle.wait()
-            return None
-        handle.wait()
+            return None, None
         slot = self.recv[self.rank + 1]
-        n = int(count_hint) if count_hint is not None else int(slot[self.max_boxes, 0].item())
-        return slot[:n]
+        return slot[:self.max_boxes], slot.view(torch.int32)[self.max_boxes, :1]
 
 
 class ShardedVideoPostProcessor(object):
     """The per-rank step of the multi-GPU pipeline: NMS of the local frames, boundary exchange,
-    link (local frames + halo).  Weak scaling: every rank holds ``n_frames`` frames."""
+    link (local frames + halo).  Weak scaling: every rank holds up to ``n_frames`` frames."""
 
-    def __init__(self, n_frames, n_boxes, n_classes, nms_thresh=0.3, device=None, group=None, n_chunks=8):
+    def __init__(self, n_frames, n_boxes, n_classes, nms_thresh=0.3, device=None, group=None, n_chunks=8, n_slots=2,
+                 n_stage=None, bind_cpus=False, stage_threads=0):
         from .vdet.video_det import VideoPostProcessor
-        self.pp = VideoPostProcessor(n_frames, n_boxes, n_classes, nms_thresh, device, n_chunks=n_chunks)
-        self.exchange = BoundaryExchange(n_boxes, self.pp.device, group)
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if bind_cpus and world > 1:
+            import os
+            local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+            local_rank = int(os.environ.get("LOCAL_RANK", dist.get_rank(group) % local_world))
+            self.cpus = bind_rank_cpus(local_rank, local_world)
+            if not stage_threads:
+                stage_threads = max(1, min(8, len(self.cpus)))
+        self.pp = VideoPostProcessor(n_frames, n_boxes, n_classes, nms_thresh, device, n_chunks=n_chunks, n_slots=n_slots,
+                                     n_stage=n_stage, stage_threads=stage_threads)
+        # one exchange buffer set per slot: step k+1's all-gather must not overwrite the halo step k still links against
+        self.exchanges = [BoundaryExchange(n_boxes, self.pp.device, group) for _ in self.pp.slots]
+        self.exchange = self.exchanges[0]
         self.side = torch.cuda.Stream(device=self.pp.device, priority=-1)
         self.n_boxes = n_boxes
         if self.exchange.world > 1:
@@ -82,13 +111,12 @@ class ShardedVideoPostProcessor(object):
             _lib.load().vdet_set_reserved_sms(2)       # room for the all-gather next to the NMS grid
 
     def _exchange(self, d_first_frame):
-        """Boundary all-gather on the side stream; returns (halo, join) -- call join() before the link."""
+        """Boundary all-gather on the side stream; returns (halo, halo_count); join the side stream before the link."""
         main = torch.cuda.current_stream()
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
             handle = self.exchange.start(d_first_frame)
-            halo = self.exchange.finish(handle, count_hint=self.n_boxes)
-        return halo
+            return self.exchange.finish(handle)
 
     def step_device(self, d_boxes, d_scores):
         """Device-resident inputs; returns the result dict of VideoPostProcessor.run_device.
@@ -96,7 +124,8 @@ class ShardedVideoPostProcessor(object):
 
         The boundary all-gather is enqueued first, on a side stream, and overlaps the NMS kernel: with
         more than one rank a few SMs are kept out of the persistent NMS grid (vdet_set_reserved_sms)
-        so that the NCCL kernel is scheduled immediately; the link kernel then waits on it.
+        so that the NCCL kernel is scheduled immediately; the link kernel then waits on it.  Successors of
+        the last frame are ``T*N + index into the neighbour's first frame``.
 
         Measured alternatives that did not pay (2 x B200, profiles/r01_scaling.md): linking the
         shard's own frames first and only the last frame after the exchange (0.55-0.56 ms/step
@@ -107,38 +136,45 @@ class ShardedVideoPostProcessor(object):
         if self.exchange.world == 1:
             return pp.run_device(d_boxes, d_scores, None, graph=True)
         main = torch.cuda.current_stream()
-        halo = self._exchange(d_boxes[:self.n_boxes])
+        halo, halo_count = self._exchange(d_boxes[:self.n_boxes])
+        pp.status.zero_()
         out = ops.nms_frames(d_boxes, d_scores, pp.seg_offsets, pp.nms_thresh, pp.N, want_mask=True,
                              status=pp.status, frame_major_out=True, out=(pp.d_idx, pp.d_cnt, pp.d_mask))
         main.wait_stream(self.side)
-        succ, link_iou = ops.link_frames(d_boxes, pp.seg_offsets, pp.N, halo, out=(pp.d_succ, pp.d_iou))
+        succ, link_iou = ops.link_frames(d_boxes, pp.seg_offsets, pp.N, halo, halo_row_base=pp.T * pp.N,
+                                         out=(pp.d_succ, pp.d_iou), halo_count=halo_count)
         res = pp._views(out)
         res.update(succ=succ, link_iou=link_iou)
         return res
 
-    def step_host(self, graph=False):
-        """The end-to-end step, synchronous: pipelined H2D from the pinned staging buffers (fill them
-        with ``self.pp.stage(boxes, scores)``), kernels + boundary exchange, D2H of the results."""
-        return self.collect(self.submit_host(graph))
+    def _halo_fn(self, slot_index, h_first_frame):
+        """Boundary exchange of one staged step, enqueued on the current (launch) stream ahead of the step:
+        the first frame goes up on its own (a few KB from the pinned upload buffer), the all-gather runs, and
+        the step -- eager or a CUDA graph -- links against this slot's fixed halo buffer."""
+        ex = self.exchanges[slot_index]
+        return ex.finish(ex.start(h_first_frame))
 
-    def submit_host(self, graph=False):
-        """Enqueue one end-to-end step without waiting for it; returns a ticket for :meth:`collect`.
-        Two steps may be in flight (double-buffered device and result buffers), which keeps the
-        host->device link busy across step boundaries.  ``graph`` (single rank only): replay the
-        step from one CUDA graph."""
+    def submit_host(self, boxes, scores, counts=None, graph=True):
+        """Enqueue one end-to-end step from host arrays (pageable or not) without waiting for it; returns a
+        ticket for :meth:`collect`.  ``n_slots`` steps may be in flight (double-buffered pinned, device and
+        result buffers), which keeps the host->device link busy across step boundaries."""
         multi = self.exchange.world > 1
-        return self.pp.submit_staged(halo_fn=self._halo_then_join if multi else None, graph=graph and not multi)
+        return self.pp.submit_host(boxes, scores, counts, halo_fn=self._halo_fn if multi else None, graph=graph)
+
+    def submit_staged(self, graph=True):
+        """The same from inputs already staged with ``self.pp.stage(...)`` (re-submission of one shard)."""
+        multi = self.exchange.world > 1
+        return self.pp.submit_staged(halo_fn=self._halo_fn if multi else None, graph=graph)
+
+    def step_host(self, boxes=None, scores=None, counts=None, graph=False):
+        """The end-to-end step, synchronous (host arrays, or the staged shard when none are given)."""
+        if boxes is None:
+            return self.collect(self.submit_staged(graph))
+        return self.collect(self.submit_host(boxes, scores, counts, graph))
 
     def collect(self, ticket):
-        """Wait for a submitted step; host views of its results (valid until the slot is reused)."""
+        """Wait for a submitted step; a StepResult of host views (valid until the slot is reused)."""
         return self.pp.collect(ticket)
-
-    def _halo_then_join(self, d_first_frame):
-        halo = self._exchange(d_first_frame)
-        # the compute stream must not start the link before the all-gather finished; the wait is
-        # enqueued now (cheap: the exchange is ~20 us and the NMS chunks run in between anyway)
-        torch.cuda.current_stream().wait_stream(self.side)
-        return halo
 
 
 def sharded_vid_nms(dets_local, thresh, row_offset, group=None):

@@ -270,10 +270,13 @@ def iou_bitmask(boxes, thresh, status=None):
     return mask, status
 
 
-def link_frames(boxes, seg_offsets, max_seg_len, halo=None, halo_row_base=0, out=None):
+def link_frames(boxes, seg_offsets, max_seg_len, halo=None, halo_row_base=0, out=None, halo_count=None):
     """Frame-to-frame link: for each box, the FIRST arg-max IoU box of the next frame.
     Returns (succ i32 [n] packed row of the successor / halo_row_base + halo index / -1,
-    best_iou f32 [n]).  ``out=(succ, best_iou)`` writes into caller-provided buffers."""
+    best_iou f32 [n]).  ``out=(succ, best_iou)`` writes into caller-provided buffers.
+    ``halo_count``: optional int32 CUDA tensor [1] with the halo's box count (``halo`` is then a
+    buffer of that capacity; ragged shards learn the count from the boundary exchange).
+    A shard passes ``halo_row_base = n`` so that halo successors are >= n (see follow_links)."""
     lib = _lib.load()
     _need(boxes, "boxes", torch.float32, 2)
     _need(seg_offsets, "seg_offsets", torch.int32, 1)
@@ -289,8 +292,11 @@ def link_frames(boxes, seg_offsets, max_seg_len, halo=None, halo_row_base=0, out
         _need(halo, "halo", torch.float32, 2)
         halo = halo.contiguous()
         n_halo = halo.shape[0]
+    if halo_count is not None:
+        _need(halo_count, "halo_count", torch.int32)
     rc = lib.vdet_link_frames_f32(_ptr(boxes), _ptr(seg_offsets), seg_offsets.numel() - 1, int(max_seg_len),
-                                  _ptr(halo), n_halo, int(halo_row_base), _ptr(succ), _ptr(best), n, _stream())
+                                  _ptr(halo), n_halo, _ptr(halo_count), int(halo_row_base), _ptr(succ), _ptr(best),
+                                  n, _stream())
     _lib.check(rc, "link_frames")
     return succ, best
 
@@ -417,14 +423,15 @@ def tubelet_interpolate(knot_x, knot_y, knot_off, dense_first, dense_off):
 
 def follow_links(succ, link_iou, start_rows, n_frames, min_iou=0.0):
     """Follow the frame-to-frame links from ``start_rows`` for ``n_frames`` frames.
-    Returns chain_rows i32 [n_frames, K] (packed row per frame, -1 after a chain ended)."""
+    Returns chain_rows i32 [n_frames, K] (packed row per frame, -1 after a chain ended).  A successor
+    >= succ.numel() is a halo index (the chain leaves this shard) and ends the chain here."""
     lib = _lib.load()
     _need(succ, "succ", torch.int32, 1)
     _need(link_iou, "link_iou", torch.float32, 1)
     _need(start_rows, "start_rows", torch.int32, 1)
     K = start_rows.numel()
     out = torch.empty((int(n_frames), K), dtype=torch.int32, device=succ.device)
-    _lib.check(lib.vdet_follow_links(_ptr(succ), _ptr(link_iou), _ptr(start_rows), K, int(n_frames), float(min_iou),
+    _lib.check(lib.vdet_follow_links(_ptr(succ), _ptr(link_iou), succ.numel(), _ptr(start_rows), K, int(n_frames), float(min_iou),
                                      _ptr(out), _stream()), "follow_links")
     return out
 

@@ -55,114 +55,145 @@ def threshold_topk_frames(scores, boxes, thresh=0.05, max_per_image=100):
     return all_boxes
 
 
+class StepResult(dict):
+    """Host results of one step (views of the slot's pinned buffers, valid until the slot is reused):
+
+      keep_off  [T*C + 1] int32  prefix offsets of the keep lists in (frame, class) order
+      keep_idx  [sum K]   uint16 kept boxes of every (frame, class) as indices WITHIN the frame, each list in
+                                 descending score -- the order utils/nms.pyx:43-66 returns per problem
+      keep_cnt  [T, C]    int32  survivors per (frame, class) (= diff of keep_off)
+      keep_bits [T*C, W]  uint32 (only with ``want_bits``) bit i of block (t, c): box i of frame t kept
+      succ      [rows]    int32  packed row of the best-IoU box in the next frame; -1: none; >= rows:
+                                 rows + index into the next shard's first frame (the chain leaves this shard)
+      link_iou  [rows]    float32 that IoU
+    """
+
+    def keep_list(self, t, c):
+        """Kept boxes of frame ``t``, class ``c`` (indices within the frame, descending score)."""
+        k = t * self["n_classes"] + c
+        return self["keep_idx"][self["keep_off"][k]:self["keep_off"][k + 1]]
+
+    def keep_mask(self):
+        """uint8 [T, C, N] mask rebuilt on the host from the keep lists (uniform frames; a convenience for
+        tests and small inputs -- the lists ARE the result)."""
+        T, C, N = self["n_frames"], self["n_classes"], self["max_boxes"]
+        cnt = self["keep_cnt"].reshape(-1)
+        blk = np.repeat(np.arange(T * C, dtype=np.int64), cnt)
+        m = np.zeros((T * C, N), np.uint8)
+        m[blk, self["keep_idx"].astype(np.int64)] = 1
+        return m.reshape(T, C, N)
+
+
 class _Slot(object):
-    """Device inputs / outputs, pinned result buffers and the completion event of ONE in-flight step."""
+    """Pinned upload buffers, device inputs / outputs, pinned result buffers and the completion event of ONE
+    in-flight step."""
 
     def __init__(self, pp, stage_set=0):
         T, N, C, dev = pp.T, pp.N, pp.C, pp.device
         rows = T * N
         self.stage_set = stage_set                          # which pinned upload buffers this slot reads
         self.h_boxes, self.h_scores = pp.h_boxes_sets[stage_set], pp.h_scores_sets[stage_set]
+        self.h_seg = pp.h_seg_sets[stage_set]
         self.d_boxes = torch.empty((rows, 4), dtype=torch.float32, device=dev)
         self.d_scores = torch.empty((rows, C), dtype=torch.float32, device=dev)
+        self.d_seg = ops.seg_offsets_uniform(T, N, dev)     # rewritten per step for ragged shards
         self.d_idx = torch.empty(rows * C, dtype=torch.int32, device=dev)
-        self.d_mask = torch.empty(rows * C, dtype=torch.uint8, device=dev)
+        self.d_mask = torch.empty(rows * C, dtype=torch.uint8, device=dev)      # device-resident entry only
         self.d_cnt = torch.empty((T, C), dtype=torch.int32, device=dev)
+        self.d_off = torch.empty(T * C + 1, dtype=torch.int32, device=dev)
         self.d_succ = torch.empty(rows, dtype=torch.int32, device=dev)
         self.d_iou = torch.empty(rows, dtype=torch.float32, device=dev)
-        self.h_mask = torch.empty(rows * C, dtype=torch.uint8).pin_memory()
-        self.h_cnt = torch.empty((T, C), dtype=torch.int32).pin_memory()
+        # results: the keep lists and their offsets are written by the compaction kernels straight into
+        # these pinned (device-mapped) buffers; succ / link_iou / status come home by copy engine
+        self.h_keep = torch.empty(rows * C, dtype=torch.uint16).pin_memory()
+        self.h_off = torch.zeros(T * C + 1, dtype=torch.int32).pin_memory()
+        self.h_bits = torch.zeros((T * C, pp.W), dtype=torch.int32).pin_memory() if pp.want_bits else None
         self.h_succ = torch.empty(rows, dtype=torch.int32).pin_memory()
         self.h_iou = torch.empty(rows, dtype=torch.float32).pin_memory()
         self.status = ops.new_status(dev)
         self.h_status = torch.zeros(1, dtype=self.status.dtype).pin_memory()
         self.ev_boxes = torch.cuda.Event()
         self.ev_link = torch.cuda.Event()
+        self.ev_nms = torch.cuda.Event()
         self.done = torch.cuda.Event()
         self.busy = False
-        self.graph = None                                   # whole-step CUDA graph (single rank)
+        self.shape = None                                   # (n_frames, rows) of the step in flight
+        self.graph = None                                   # whole-step CUDA graph (uniform frames)
         self.launch_stream = torch.cuda.Stream(device=dev)  # the graph of this slot is launched here
         # frames of more than 1024 boxes keep their bit matrix in a global scratch slot per CTA
-        ws_bytes = _lib.load().vdet_nms_frames_workspace_bytes(N, C, dev.index or 0) if N > 1024 else 0
-        self.ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
-        ws_ptr = self.ws.data_ptr() if ws_bytes else None
-        # per pipeline chunk: views of every buffer + the prebuilt argument list of the NMS launch
-        self.chunks = []
-        for f0, f1 in pp.chunks:
-            r0, r1 = f0 * N, f1 * N
-            d_sc = self.d_scores[r0:r1]
-            d_idx, d_mask, d_cnt = self.d_idx[r0 * C:r1 * C], self.d_mask[r0 * C:r1 * C], self.d_cnt[f0:f1]
-            seg = pp.chunk_seg[f1 - f0]
-            nms_args = (self.d_boxes[r0:r1].data_ptr(), 4, d_sc.data_ptr(), C, 1, seg.data_ptr(), f1 - f0, N, None, C,
-                        pp.nms_thresh, d_idx.data_ptr(), d_cnt.data_ptr(), d_mask.data_ptr(), r1 - r0,
-                        _lib.LAYOUT_FRAME_MAJOR, self.status.data_ptr(), ws_ptr, ws_bytes)
-            self.chunks.append({
-                "d_scores": d_sc, "h_scores": self.h_scores[r0:r1], "nms_args": nms_args,
-                "d_mask": d_mask, "h_mask": self.h_mask[r0 * C:r1 * C], "d_cnt": d_cnt, "h_cnt": self.h_cnt[f0:f1],
-                "ev_in": torch.cuda.Event(), "ev_nms": torch.cuda.Event()})
-
-    def host_views(self, pp):
-        return {"keep_mask": self.h_mask.numpy().reshape(pp.T, pp.C, pp.N), "keep_cnt": self.h_cnt.numpy(),
-                "succ": self.h_succ.numpy(), "link_iou": self.h_iou.numpy()}
+        self.ws_bytes = _lib.load().vdet_nms_frames_workspace_bytes(N, C, dev.index or 0) if N > 1024 else 0
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev) if self.ws_bytes else None
+        self.ev_in = [torch.cuda.Event() for _ in range(pp.n_chunks)]
 
 
 class VideoPostProcessor(object):
-    """NMS (all classes) + frame-to-frame link for one video shard of fixed shape.
+    """NMS (all classes) + frame-to-frame link for one video shard of up to ``n_frames`` frames of up to
+    ``n_boxes`` boxes.
 
-    Input: boxes [T, N, 4] float32 and scores [T, N, C] float32 on the HOST (any array-like;
-    copied through pinned staging buffers) or already on the device.  Output (device tensors from
-    :meth:`run_device`, host arrays from :meth:`run_host` / :meth:`run_staged` / :meth:`collect`),
-    frame-major:
+    Input: boxes [T, N, 4] and scores [T, N, C] float32 on the HOST -- any C-contiguous arrays, pageable
+    memory included; every step copies them through the processor's pinned upload buffers -- or already on
+    the device (:meth:`run_device`).  Ragged shards pass packed rows [sum n_t, 4] / [sum n_t, C] plus
+    ``counts`` [T'] (boxes per frame, T' <= n_frames, every n_t <= n_boxes).  Host output: a
+    :class:`StepResult` -- the ordered keep lists of every (frame, class), i.e. what ``apply_vid_nms`` returns
+    for every class (vdet/video_det.py:51-61, utils/nms.pyx:43-66), and the link.
 
-      keep_mask [T, C, N] uint8   1 = detection survives per-frame NMS for that class
-      keep_cnt  [T, C]    int32   survivors per (frame, class)
-      keep_idx  [T, C, N] int32   surviving rows of the frame in descending score, -1 padded
-                                  (device only; not copied back by default)
-      succ      [T*N]     int32   packed row of the best-IoU box in the next frame (-1: none)
-      link_iou  [T*N]     float32 that IoU
+    ``halo`` (boxes of the first frame of the NEXT shard, [H,4], optional ``halo_count`` on the device) links
+    the shard's last frame across a shard boundary (see vdetlib_b200.dist); halo successors are reported as
+    ``rows + index``.
 
-    ``halo`` (boxes of the first frame of the NEXT shard, [H,4]) links the shard's last frame
-    across a shard boundary (see vdetlib_b200.dist).
-
-    The host path is pipelined twice over.  Inside a step the shard is cut into ``n_chunks`` frame
-    ranges; chunk k's host->device copy (copy stream), NMS (compute stream) and result read-back
-    (read-back stream) overlap with the neighbouring chunks', so PCIe in both directions and the SMs
-    are busy at the same time (frame-major outputs make every chunk a contiguous byte range).
-    Across steps, :meth:`submit_staged` / :meth:`collect` keep up to ``n_slots`` steps in flight, each
-    with its own device and result buffers: the upload of step k+1 starts while the last NMS chunk
-    and read-back of step k are still running, so the host->device link -- the bound of this path --
-    never idles.  On a single rank a whole step can also be replayed from one CUDA graph
-    (``graph=True``): one launch per step instead of ~50 stream operations.
+    The host path is pipelined twice over.  Inside a step the score block is cut into ``n_chunks`` frame
+    ranges; chunk k's host->device copy (copy stream) overlaps the NMS of the chunks before it (compute
+    stream), the link and its read-back run under the score upload, and the keep lists go home from the
+    compaction kernel itself (stores to mapped pinned memory: sum K is data dependent, a copy-engine D2H would
+    need it on the host first).  Across steps, :meth:`submit_host` / :meth:`collect` keep up to ``n_slots``
+    steps in flight, each with its own pinned, device and result buffers: while the host streams shard k+1
+    into its upload buffers, shard k is uploading / computing.  Uniform shards replay the whole step from one
+    CUDA graph per slot (one launch instead of ~40 stream operations).
     """
 
-    def __init__(self, n_frames, n_boxes, n_classes, nms_thresh=0.3, device=None, n_chunks=8, n_slots=2, n_stage=1):
+    def __init__(self, n_frames, n_boxes, n_classes, nms_thresh=0.3, device=None, n_chunks=8, n_slots=2, n_stage=None,
+                 want_bits=False, stage_threads=0):
         self.T, self.N, self.C = int(n_frames), int(n_boxes), int(n_classes)
         self.nms_thresh = float(nms_thresh)
         self.device = device or ops.default_device()
+        self.want_bits = bool(want_bits)
+        self.stage_threads = int(stage_threads)
+        self.W = (self.N + 31) // 32
         T, N, C = self.T, self.N, self.C
         rows = T * N
         dev = self.device
         self.seg_offsets = ops.seg_offsets_uniform(T, N, dev)
-        # pinned upload buffers: one set shared by every slot (n_stage=1: the staged shard can be submitted any
-        # number of times), or one set per slot (n_stage=n_slots: shard k+1 is staged while shard k is in flight)
+        self._uniform_off = np.arange(0, (T + 1) * N, N, dtype=np.int32)
+        # pinned upload buffers: one set per slot (shard k+1 is staged while shard k is in flight), or one set
+        # shared by every slot (n_stage=1: a staged shard can be submitted any number of times)
         n_slots = max(1, int(n_slots))
-        if int(n_stage) not in (1, n_slots):
+        n_stage = n_slots if n_stage is None else int(n_stage)
+        if n_stage not in (1, n_slots):
             raise ValueError("n_stage must be 1 or n_slots")
-        self.n_stage = int(n_stage)
-        self.h_boxes_sets = [torch.empty((rows, 4), dtype=torch.float32).pin_memory() for _ in range(self.n_stage)]
-        self.h_scores_sets = [torch.empty((rows, C), dtype=torch.float32).pin_memory() for _ in range(self.n_stage)]
+        self.n_stage = n_stage
+        self.h_boxes_sets = [torch.empty((rows, 4), dtype=torch.float32).pin_memory() for _ in range(n_stage)]
+        self.h_scores_sets = [torch.empty((rows, C), dtype=torch.float32).pin_memory() for _ in range(n_stage)]
+        self.h_seg_sets = [torch.from_numpy(self._uniform_off.copy()).pin_memory() for _ in range(n_stage)]
+        self._staged = [None] * n_stage                     # per staging set: (n_frames, rows, uniform) of its shard
         self.h_boxes, self.h_scores = self.h_boxes_sets[0], self.h_scores_sets[0]
-        # frame ranges of the pipeline chunks
-        n_chunks = max(1, min(int(n_chunks), T))
-        edges = [round(k * T / n_chunks) for k in range(n_chunks + 1)]
-        self.chunks = [(edges[k], edges[k + 1]) for k in range(n_chunks) if edges[k + 1] > edges[k]]
-        self.chunk_seg = {f1 - f0: ops.seg_offsets_uniform(f1 - f0, N, dev) for f0, f1 in self.chunks}
+        # frame ranges of the pipeline chunks (uniform shards; ragged ones balance rows per step)
+        self.n_chunks = max(1, min(int(n_chunks), T))
+        self.chunks = self._chunk_edges(self._uniform_off, T)
         self.s_in = torch.cuda.Stream(device=dev)
         self.s_out = torch.cuda.Stream(device=dev)
         self.slots = [_Slot(self, k % self.n_stage) for k in range(n_slots)]
         self._next_slot = 0
         self._graphs = {}
         self._lib = _lib.load()
+
+    def _chunk_edges(self, off, n_frames):
+        """Frame ranges whose row counts are as equal as the frame boundaries allow."""
+        rows = int(off[n_frames])
+        k = max(1, min(self.n_chunks, n_frames))
+        targets = (np.arange(1, k) * rows) // k
+        cuts = np.searchsorted(off[:n_frames + 1], targets, side="left")
+        edges = sorted(set([0, n_frames] + [int(c) for c in cuts]))
+        return [(edges[i], edges[i + 1]) for i in range(len(edges) - 1) if edges[i + 1] > edges[i]]
 
     # slot 0 doubles as the buffer set of the synchronous / device-resident entry points
     d_boxes = property(lambda self: self.slots[0].d_boxes)
@@ -172,37 +203,39 @@ class VideoPostProcessor(object):
     d_cnt = property(lambda self: self.slots[0].d_cnt)
     d_succ = property(lambda self: self.slots[0].d_succ)
     d_iou = property(lambda self: self.slots[0].d_iou)
-    h_mask = property(lambda self: self.slots[0].h_mask)
-    h_cnt = property(lambda self: self.slots[0].h_cnt)
-    h_succ = property(lambda self: self.slots[0].h_succ)
-    h_iou = property(lambda self: self.slots[0].h_iou)
     status = property(lambda self: self.slots[0].status)
     h_status = property(lambda self: self.slots[0].h_status)
 
-    # bytes crossing PCIe per staged step
+    # bytes crossing PCIe per full-size step: uploads are fixed, the keep lists are data dependent
     @property
     def h2d_bytes(self):
         return self.h_boxes.numel() * 4 + self.h_scores.numel() * 4
 
-    @property
-    def d2h_bytes(self):
-        sl = self.slots[0]
-        return sl.h_mask.numel() + sl.h_cnt.numel() * 4 + sl.h_succ.numel() * 4 + sl.h_iou.numel() * 4
+    def d2h_bytes(self, result):
+        """Bytes the step behind ``result`` sent home: keep lists + offsets + link + status (+ bit masks)."""
+        rows = int(result["succ"].shape[0])
+        b = 2 * int(result["keep_off"][-1]) + 4 * int(result["keep_off"].shape[0]) + 8 * rows + 4
+        if "keep_bits" in result:
+            b += 4 * int(result["keep_bits"].size)
+        return b
 
     def _views(self, out):
         T, N, C = self.T, self.N, self.C
         return {"keep_idx": out[0].view(T, C, N), "keep_cnt": out[1], "keep_mask": out[2].view(T, C, N)}
 
-    def _launch(self, d_boxes, d_scores, halo):
+    def _launch(self, d_boxes, d_scores, halo, halo_count=None):
+        self.status.zero_()
         out = ops.nms_frames(d_boxes, d_scores, self.seg_offsets, self.nms_thresh, self.N, want_mask=True,
                              status=self.status, frame_major_out=True, out=(self.d_idx, self.d_cnt, self.d_mask))
-        ops.link_frames(d_boxes, self.seg_offsets, self.N, halo, out=(self.d_succ, self.d_iou))
+        ops.link_frames(d_boxes, self.seg_offsets, self.N, halo, halo_row_base=self.T * self.N,
+                        out=(self.d_succ, self.d_iou), halo_count=halo_count)
         return out
 
     def run_device(self, d_boxes, d_scores, halo=None, graph=False):
-        """Device tensors in ([T*N,4], [T*N,C]), device tensors out; asynchronous.
+        """Device tensors in ([T*N,4], [T*N,C]), device tensors out (padded keep_idx [T,C,N], keep_cnt,
+        keep_mask, succ, link_iou); asynchronous.
 
-        ``graph=True`` replays the two launches (NMS, link) from a CUDA graph captured on first use for
+        ``graph=True`` replays the launches (NMS, link) from a CUDA graph captured on first use for
         this pair of input buffers -- no per-step launch overhead or inter-kernel gap.  Outputs always
         live in the processor's own buffers (slot 0; valid until the next call)."""
         if not graph:
@@ -223,61 +256,97 @@ class VideoPostProcessor(object):
         res.update(succ=self.d_succ, link_iou=self.d_iou)
         return res
 
-    def stage(self, boxes, scores):
-        """Copy host arrays into the pinned upload buffers of the NEXT step to be submitted (not part of the
-        timed region) with streaming stores: lines written with ordinary stores stay dirty in the CPU caches and
-        the copy engine then reads them at roughly half the PCIe rate (profiles/r01_pcie.md).
-        With one staging set (``n_stage=1``) every step in flight reads these buffers: collect all outstanding
-        steps before restaging.  With a set per slot only the slot about to be reused must have been collected."""
-        b = np.ascontiguousarray(boxes, dtype=np.float32).reshape(-1, 4)
-        s = np.ascontiguousarray(scores, dtype=np.float32).reshape(-1, self.C)
-        if b.shape[0] != self.h_boxes.shape[0] or s.shape[0] != self.h_scores.shape[0]:
-            raise ValueError("stage: expected %d rows" % self.h_boxes.shape[0])
+    # ---- staging ---------------------------------------------------------------------------
+    def _target_slot(self):
         if not any(sl.busy for sl in self.slots):
             self._next_slot = 0
-        target = self.slots[self._next_slot]
+        return self.slots[self._next_slot]
+
+    def stage(self, boxes, scores, counts=None):
+        """Copy host arrays (pageable or not) into the pinned upload buffers of the NEXT step to be submitted,
+        with streaming stores over several host threads: lines written with ordinary stores stay dirty in the
+        CPU caches and the copy engine then reads them at roughly half the PCIe rate (profiles/r01_pcie.md).
+        With one staging set (``n_stage=1``) every step in flight reads these buffers: collect all outstanding
+        steps before restaging.  With a set per slot only the slot about to be reused must have been collected."""
+        target = self._target_slot()
         if any(sl.busy and sl.stage_set == target.stage_set for sl in self.slots):
             raise RuntimeError("stage: a submitted step still reads the staging buffers; collect() it first")
-        ops.host_copy_stream(target.h_boxes, b)
-        ops.host_copy_stream(target.h_scores, s)
+        b = np.ascontiguousarray(boxes, dtype=np.float32).reshape(-1, 4)
+        s = np.ascontiguousarray(scores, dtype=np.float32).reshape(-1, self.C)
+        if counts is None:
+            n_frames, rows, uniform = self.T, self.T * self.N, True
+            if b.shape[0] != rows or s.shape[0] != rows:
+                raise ValueError("stage: expected %d rows" % rows)
+            if self._staged[target.stage_set] is not None and not self._staged[target.stage_set][2]:
+                target.h_seg.numpy()[:] = self._uniform_off
+        else:
+            cnt = np.asarray(counts, dtype=np.int64).reshape(-1)
+            n_frames, rows, uniform = int(cnt.shape[0]), int(cnt.sum()), False
+            if n_frames < 1 or n_frames > self.T or (cnt < 0).any() or int(cnt.max()) > self.N:
+                raise ValueError("stage: counts must describe 1..%d frames of 0..%d boxes" % (self.T, self.N))
+            if b.shape[0] != rows or s.shape[0] != rows:
+                raise ValueError("stage: counts add up to %d rows, got %d / %d" % (rows, b.shape[0], s.shape[0]))
+            seg = target.h_seg.numpy()
+            seg[0] = 0
+            np.cumsum(cnt, out=seg[1:n_frames + 1])
+            seg[n_frames + 1:] = rows
+        if rows:
+            ops.host_copy_stream(target.h_boxes[:rows], b, self.stage_threads)
+            ops.host_copy_stream(target.h_scores[:rows], s, self.stage_threads)
+        self._staged[target.stage_set] = (n_frames, rows, uniform)
 
-    def _enqueue(self, sl, halo, halo_fn, fork):
-        """Stream operations of one staged step on slot ``sl``.  The boxes (4 floats/row) go first, so
-        the link -- which needs no scores -- and its D2H run under the upload of the scores
-        (C floats/row); each score chunk is followed by its NMS launch and the download of its keep
-        mask.  ``fork``: branch the copy streams off the current stream and join them again (what a
-        stream capture needs); otherwise the copy streams run free and ``sl.done`` marks the end."""
-        N = self.N
+    # ---- one step on the streams -----------------------------------------------------------
+    def _enqueue(self, sl, shape, halo, halo_count, fork):
+        """Stream operations of one staged step on slot ``sl``.  The boxes (4 floats/row) go first, so the
+        link -- which needs no scores -- and its D2H run under the upload of the scores (C floats/row); each
+        score chunk is followed by its NMS launch; the compaction of the keep lists writes them home.
+        ``fork``: branch the copy streams off the current stream and join them again (what a stream capture
+        needs); otherwise the copy streams run free and ``sl.done`` marks the end."""
+        n_frames, rows, uniform = shape
+        N, C = self.N, self.C
         cur = torch.cuda.current_stream()
         s_in, s_out = self.s_in, self.s_out
+        off = self._uniform_off if uniform else sl.h_seg.numpy()
+        chunks = self.chunks if uniform else self._chunk_edges(off, n_frames)
         if fork:
             s_in.wait_stream(cur)
             s_out.wait_stream(cur)
+        sl.status.zero_()                                   # a flagged shard must not poison the next one
         with torch.cuda.stream(s_in):
-            sl.d_boxes.copy_(sl.h_boxes, non_blocking=True)
+            sl.d_seg.copy_(sl.h_seg, non_blocking=True)       # 4 KB: the step's segment table (uniform or ragged)
+            if rows:
+                sl.d_boxes[:rows].copy_(sl.h_boxes[:rows], non_blocking=True)
             sl.ev_boxes.record(s_in)
-            for ch in sl.chunks:
-                ch["d_scores"].copy_(ch["h_scores"], non_blocking=True)
-                ch["ev_in"].record(s_in)
+            for k, (f0, f1) in enumerate(chunks):
+                r0, r1 = int(off[f0]), int(off[f1])
+                if r1 > r0:
+                    sl.d_scores[r0:r1].copy_(sl.h_scores[r0:r1], non_blocking=True)
+                sl.ev_in[k].record(s_in)
         cur.wait_event(sl.ev_boxes)
-        if halo_fn is not None:
-            halo = halo_fn(sl.d_boxes[:N])
-        ops.link_frames(sl.d_boxes, self.seg_offsets, N, halo, out=(sl.d_succ, sl.d_iou))
+        seg = sl.d_seg[:n_frames + 1]
+        ops.link_frames(sl.d_boxes[:rows], seg, N, halo, halo_row_base=rows, out=(sl.d_succ, sl.d_iou),
+                        halo_count=halo_count)
         sl.ev_link.record(cur)
         s_out.wait_event(sl.ev_link)
         with torch.cuda.stream(s_out):
-            sl.h_succ.copy_(sl.d_succ, non_blocking=True)
-            sl.h_iou.copy_(sl.d_iou, non_blocking=True)
+            sl.h_succ[:rows].copy_(sl.d_succ[:rows], non_blocking=True)
+            sl.h_iou[:rows].copy_(sl.d_iou[:rows], non_blocking=True)
         nms = self._lib.vdet_nms_frames_f32
         stream_ptr = cur.cuda_stream
-        for ch in sl.chunks:
-            cur.wait_event(ch["ev_in"])
-            _lib.check(nms(*ch["nms_args"], stream_ptr), "nms_frames")
-            ch["ev_nms"].record(cur)
-            s_out.wait_event(ch["ev_nms"])
-            with torch.cuda.stream(s_out):
-                ch["h_mask"].copy_(ch["d_mask"], non_blocking=True)
-                ch["h_cnt"].copy_(ch["d_cnt"], non_blocking=True)
+        ws_ptr = sl.ws.data_ptr() if sl.ws is not None else None
+        for k, (f0, f1) in enumerate(chunks):
+            cur.wait_event(sl.ev_in[k])
+            # absolute row offsets: every chunk passes the shard's base pointers and its own slice of the
+            # segment table / count table
+            _lib.check(nms(sl.d_boxes.data_ptr(), 4, sl.d_scores.data_ptr(), C, 1, sl.d_seg[f0:].data_ptr(), f1 - f0, N,
+                           None, C, self.nms_thresh, sl.d_idx.data_ptr(), sl.d_cnt[f0:].data_ptr(), None, rows,
+                           _lib.LAYOUT_FRAME_MAJOR, sl.status.data_ptr(), ws_ptr, sl.ws_bytes, stream_ptr), "nms_frames")
+        _lib.check(self._lib.vdet_compact_keep(sl.d_idx.data_ptr(), sl.d_cnt.data_ptr(), sl.d_seg.data_ptr(), n_frames, N, C,
+                                               _lib.KEEP_U16_LOCAL, sl.d_off.data_ptr(), sl.h_off.data_ptr(),
+                                               sl.h_keep.data_ptr(), sl.h_bits.data_ptr() if sl.h_bits is not None else None,
+                                               stream_ptr), "compact_keep")
+        sl.ev_nms.record(cur)
+        s_out.wait_event(sl.ev_nms)
         with torch.cuda.stream(s_out):
             sl.h_status.copy_(sl.status, non_blocking=True)
         if fork:
@@ -286,57 +355,87 @@ class VideoPostProcessor(object):
         else:
             sl.done.record(s_out)
 
-    def _capture(self, sl):
+    def _capture(self, sl, shape, halo, halo_count):
         """Capture the whole staged step of slot ``sl`` (copies on three streams + kernels) into one graph."""
         with torch.cuda.stream(sl.launch_stream):
-            self._enqueue(sl, None, None, fork=True)      # warm-up: kernel attributes are set outside the capture
+            self._enqueue(sl, shape, halo, halo_count, fork=True)     # warm-up: kernel attributes are set outside the capture
         sl.launch_stream.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=sl.launch_stream):
-            self._enqueue(sl, None, None, fork=True)
+            self._enqueue(sl, shape, halo, halo_count, fork=True)
         sl.graph = g
+        sl.graph_key = (0 if halo is None else halo.data_ptr(), 0 if halo_count is None else halo_count.data_ptr())
 
-    def submit_staged(self, halo=None, halo_fn=None, graph=False):
-        """Enqueue one step on the next free slot and return a ticket for :meth:`collect`; does not block.
-        Up to ``n_slots`` steps may be in flight.  ``halo_fn(d_first_frame_boxes)`` (optional) is called
-        on the compute stream once the boxes are on the device and returns the halo tensor (boundary
-        exchange).  ``graph=True`` (no halo) replays the step from a CUDA graph captured on first use."""
+    def submit_staged(self, halo=None, halo_fn=None, graph=False, halo_count=None):
+        """Enqueue one step on the next free slot from its staged inputs and return a ticket for
+        :meth:`collect`; does not block.  Up to ``n_slots`` steps may be in flight.
+
+        ``halo_fn(slot_index, h_first_frame_boxes)`` (optional) runs the boundary exchange for this step
+        before anything else is enqueued and returns ``(halo, halo_count)`` device tensors (fixed addresses
+        per slot, so the step's graph can hold them).  ``graph=True`` replays the step from a CUDA graph
+        captured on first use (uniform shards only; ragged ones always take the eager stream path)."""
         k = self._next_slot
         sl = self.slots[k]
         if sl.busy:
             raise RuntimeError("submit_staged: all %d slots are in flight; collect() the oldest step first"
                                % len(self.slots))
-        if graph and halo is None and halo_fn is None:
-            if sl.graph is None:
-                self._capture(sl)
+        shape = self._staged[sl.stage_set]
+        if shape is None:
+            raise RuntimeError("submit_staged: nothing staged; call stage() first")
+        n_frames, rows, uniform = shape
+        if graph and uniform:
             with torch.cuda.stream(sl.launch_stream):
+                if halo_fn is not None:
+                    halo, halo_count = halo_fn(k, sl.h_boxes[:int(self._uniform_off[1])])
+                key = (0 if halo is None else halo.data_ptr(), 0 if halo_count is None else halo_count.data_ptr())
+                if sl.graph is None or sl.graph_key != key:
+                    self._capture(sl, shape, halo, halo_count)
                 sl.graph.replay()
                 sl.done.record(sl.launch_stream)
         else:
-            self._enqueue(sl, halo, halo_fn, fork=False)
+            if halo_fn is not None:
+                first = int(sl.h_seg[1].item()) if not uniform else self.N
+                halo, halo_count = halo_fn(k, sl.h_boxes[:first])
+            self._enqueue(sl, shape, halo, halo_count, fork=False)
+        sl.shape = shape
         sl.busy = True
         self._next_slot = (k + 1) % len(self.slots)
         return k
 
+    def submit_host(self, boxes, scores, counts=None, halo=None, halo_fn=None, graph=True, halo_count=None):
+        """The user-facing asynchronous call: stage the host arrays (this is where the caller's memory is read;
+        the arrays may be reused as soon as this returns) and enqueue the step.  Returns a ticket."""
+        self.stage(boxes, scores, counts)
+        return self.submit_staged(halo, halo_fn, graph, halo_count)
+
     def collect(self, ticket):
-        """Wait for the step behind ``ticket``; returns host views of its pinned result buffers
-        (valid until the slot is submitted again) after translating the status word."""
+        """Wait for the step behind ``ticket``; returns a :class:`StepResult` of host views (valid until the
+        slot is submitted again) after translating the status word."""
         sl = self.slots[ticket]
         if not sl.busy:
             raise RuntimeError("collect: ticket %r is not in flight" % (ticket,))
         sl.done.synchronize()
         sl.busy = False
         ops.raise_for_status_word(int(sl.h_status.item()))
-        return sl.host_views(self)
+        n_frames, rows, uniform = sl.shape
+        nb = n_frames * self.C
+        off = sl.h_off.numpy()[:nb + 1]
+        res = StepResult(keep_off=off, keep_idx=sl.h_keep.numpy()[:int(off[nb])],
+                         keep_cnt=np.diff(off).reshape(n_frames, self.C),
+                         succ=sl.h_succ.numpy()[:rows], link_iou=sl.h_iou.numpy()[:rows],
+                         n_frames=n_frames, n_classes=self.C, max_boxes=self.N)
+        if sl.h_bits is not None:
+            res["keep_bits"] = sl.h_bits.numpy()[:nb].view(np.uint32)
+        return res
 
-    def run_staged(self, halo=None, halo_fn=None, graph=False):
+    def run_staged(self, halo=None, halo_fn=None, graph=False, halo_count=None):
         """One synchronous step from the staged inputs: submit + collect (on slot 0 when nothing is in flight,
         so that ``d_boxes`` / ``d_scores`` hold the step's inputs afterwards)."""
         if not any(sl.busy for sl in self.slots):
             self._next_slot = 0
-        return self.collect(self.submit_staged(halo, halo_fn, graph))
+        return self.collect(self.submit_staged(halo, halo_fn, graph, halo_count))
 
-    def run_host(self, boxes, scores, halo=None):
-        """The user-facing call: host arrays in, host arrays out."""
-        self.stage(boxes, scores)
-        return self.run_staged(halo)
+    def run_host(self, boxes, scores, counts=None, halo=None, graph=False):
+        """The user-facing synchronous call: host arrays in, host results out."""
+        self.stage(boxes, scores, counts)
+        return self.run_staged(halo, graph=graph)
