@@ -27,7 +27,7 @@ def main():
     srcs = B.sources()
 
     def one(src):
-        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(obj_dir, os.path.splitext(os.path.basename(src))[0] + ".o")
         r = subprocess.run([B._nvcc()] + B.NVCC_FLAGS + defs + ["-c", src, "-o", obj], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s" % (src, r.stderr))

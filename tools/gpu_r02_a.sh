@@ -14,7 +14,7 @@ VDET_B200_LIB=vdetlib_b200/variants/libvdet_b200_pure_lds.so python tools/nms_ti
 done
 cat gpurun_out/nms_time_product.json gpurun_out/nms_time_pure_lds.json
 el "variant parity"
-VDET_B200_LIB=vdetlib_b200/variants/libvdet_b200_pure_lds.so timeout 200 python -m pytest tests/test_gpu_nms.py -m gpu -q -x -p no:cacheprovider -k "frames_vs_oracle or tied or golden or full_config2" > gpurun_out/pytest_pure_lds.log 2>&1; tail -n 2 gpurun_out/pytest_pure_lds.log
+VDET_B200_LIB=vdetlib_b200/variants/libvdet_b200_pure_lds.so timeout 200 python -m pytest tests/test_gpu_nms.py -m gpu -q -x -p no:cacheprovider -k "frames_vs or tied or golden or full_config2" > gpurun_out/pytest_pure_lds.log 2>&1; tail -n 2 gpurun_out/pytest_pure_lds.log
 el "h2d probe N=1"
 timeout 120 python tools/h2d_scale_probe.py > gpurun_out/h2d_probe_n1.json 2>> gpurun_out/a.err; cat gpurun_out/h2d_probe_n1.json
 el "big kernel time"
@@ -35,9 +35,9 @@ el "kernel bench"
 timeout 300 python tools/kernel_bench.py > gpurun_out/kernels.txt 2>> gpurun_out/a.err; tail -n 25 gpurun_out/kernels.txt
 el "compute-sanitizer memcheck (small-frame + big-frame NMS parity tests)"
 timeout 500 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_nms.py -m gpu -q -x -p no:cacheprovider \
-    -k "frames_vs_or\acle or tied or ragged" > gpurun_out/sanitizer_memcheck.log 2>&1; tail -n 6 gpurun_out/sanitizer_memcheck.log
+    -k "frames_vs or tied or ragged" > gpurun_out/sanitizer_memcheck.log 2>&1; tail -n 6 gpurun_out/sanitizer_memcheck.log
 el "compute-sanitizer racecheck"
 timeout 600 compute-sanitizer --tool racecheck --print-limit 20 python -m pytest tests/test_gpu_nms.py -m gpu -q -x -p no:cacheprovider \
-    -k "frames_vs_or\acle or tied or ragged" > gpurun_out/sanitizer_racecheck.log 2>&1; tail -n 6 gpurun_out/sanitizer_racecheck.log
+    -k "frames_vs or tied or ragged" > gpurun_out/sanitizer_racecheck.log 2>&1; tail -n 6 gpurun_out/sanitizer_racecheck.log
 ls -la gpurun_out | head -40
 el done

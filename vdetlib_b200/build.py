@@ -37,7 +37,8 @@ def _nvcc():
 
 
 def sources():
-    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    """CUDA sources + plain host sources (nvcc hands .cpp files to the host compiler)."""
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cpp")))
 
 
 def _deps_mtime():
@@ -53,7 +54,7 @@ def needs_build():
 
 
 def _compile_one(src, verbose):
-    obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+    obj = os.path.join(OBJ, os.path.splitext(os.path.basename(src))[0] + ".o")
     if os.path.isfile(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), _deps_mtime()):
         return obj, ""
     cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]

@@ -1,5 +1,6 @@
 // api.cu -- error reporting and device queries of libvdet_b200.so.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -56,9 +57,25 @@ int max_optin_smem_cached() {
     return v > 0 ? v : 227 * 1024;
 }
 
+bool cpu_has_avx512f();                                                          // host_copy.cpp
+void copy_stream_range_512(unsigned char* d, const unsigned char* s, size_t bytes);
+
+// VDET_HOST_COPY=sse|avx512 forces a flavour (measurement hook); default: AVX-512 full-line stores when the CPU has them
+static int host_copy_flavour() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("VDET_HOST_COPY");
+        if (e && !strcmp(e, "sse")) v = 0;
+        else if (e && !strcmp(e, "avx512")) v = cpu_has_avx512f() ? 1 : 0;
+        else v = cpu_has_avx512f() ? 1 : 0;
+    }
+    return v;
+}
+
 // Non-temporal copy of one byte range (16-byte streaming stores, plain copies for the unaligned ends),
 // fenced before returning so that the stores are globally visible when the caller hands the buffer to a DMA.
 void copy_stream_range(unsigned char* d, const unsigned char* s, size_t bytes) {
+    if (host_copy_flavour() == 1) { copy_stream_range_512(d, s, bytes); return; }
     size_t head = (16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15;     // stores must be 16-byte aligned
     if (head > bytes) head = bytes;
     memcpy(d, s, head);
