@@ -16,6 +16,7 @@ The NMS family (utils/nms.pyx) lives in oracle/nms_oracle.c (C restatement) and
 oracle/_ref (the real Cython, compiled from the reference tree).
 """
 import copy
+import os
 from collections import defaultdict
 
 import numpy as np
@@ -487,3 +488,85 @@ def frame_top_detections(det_proto, top_num, class_index):
                      key=lambda x: det_score(x, class_index), reverse=True)
         out['detections'].extend(cur[:top_num])
     return out
+
+
+def rcnn_sampling_dets_scoring(vid_proto, track_proto, det_proto, net, class_idx, rcnn_model, class_names,
+                               overlap_thres=0.7, save_feat=False, save_all_sc=False, score_column=None):
+    """vdet/tubelet_cls.py:196-260 with the CNN / SVM as callables (``net(path, boxes) -> features``,
+    ``rcnn_model(features) -> scores``; ``score_column`` = ``index_vdet_to_det[class_idx] - 1`` of :217)."""
+    tubelets_proto = tubelets_proto_from_tracks_proto(track_proto['tracks'], class_idx, class_names)
+    for frame in vid_proto['frames']:
+        frame_id = frame['frame']
+        path = str(os.path.join(vid_proto['root_path'], frame['path']))
+        boxes = [next((b['bbox'] for b in t['boxes'] if b['frame'] == frame_id), None) for t in tubelets_proto]   # :205
+        valid_boxes = np.asarray([box for box in boxes if box is not None])
+        valid_index = [i for i, box in enumerate(boxes) if box is not None]
+        if len(valid_index) == 0:
+            continue
+        features = net(path, valid_boxes)                                   # :213
+        scores = np.asarray(rcnn_model(features))                           # :214
+        cls_scores = scores[:, score_column]                                # :215-218
+        dets = [det for det in det_proto['detections'] if det['frame'] == frame_id]
+        det_boxes = np.asarray([x['bbox'] for x in dets])
+        det_scores = np.asarray([det_score(x, class_idx) for x in dets])
+        for score, tubelet_id, feat, all_score in zip(cls_scores, valid_index, features, scores):
+            cur_box = [box for box in tubelets_proto[tubelet_id]['boxes'] if box['frame'] == frame_id]
+            assert len(cur_box) == 1
+            if len(det_boxes) > 0:
+                overlaps = iou([cur_box[0]['bbox']], det_boxes)
+                conf_idx = (overlaps > overlap_thres).ravel()
+            else:
+                conf_idx = [False]
+            if np.any(conf_idx):
+                conf_boxes = det_boxes[conf_idx]
+                conf_scores = det_scores[conf_idx]
+                max_idx = np.argmax(conf_scores)
+                max_score = conf_scores[max_idx]
+                max_box = conf_boxes[max_idx].tolist()
+            else:
+                max_score = -np.inf
+            if max_score > score:                                           # :239
+                cur_box[0]['det_score'] = max_score
+                cur_box[0]['bbox'] = max_box
+                max_feat = net(path, [max_box])
+                if save_feat:
+                    cur_box[0]['feat'] = np.asarray(max_feat).ravel().tolist()
+                if save_all_sc:
+                    cur_box[0]['all_score'] = np.asarray(rcnn_model(max_feat)).ravel().tolist()
+            else:
+                cur_box[0]['det_score'] = score
+                if save_feat:
+                    cur_box[0]['feat'] = np.asarray(feat).ravel().tolist()
+                if save_all_sc:
+                    cur_box[0]['all_score'] = np.asarray(all_score).ravel().tolist()
+    return tubelets_proto
+
+
+def score_conv_cls(score_proto, net):
+    """vdet/tubelet_cls.py:15-51: per tubelet, the 1-D channels go into ``(1, C, 1, L)`` blobs of ``net`` (anything with
+    Caffe's ``blobs`` / ``forward`` surface) and ``probs[:, 1, :]`` comes back as ``conv_score``."""
+    new_score_proto = copy.copy(score_proto)
+    for tubelet in new_score_proto['tubelets']:
+        track = {}
+        track['length'] = len(tubelet['boxes'])
+        track['gt'] = tubelet['gt']
+        track['mean_iou'] = np.mean([[x['gt_overlap'] for x in tubelet['boxes']]])
+        track['det_scores'] = [x['det_score'] for x in tubelet['boxes']]
+        track['track_scores'] = [x['track_score'] for x in tubelet['boxes']]
+        track['anchors'] = [x['anchor'] * 1. / track['length'] for x in tubelet['boxes']]
+        track['abs_anchors'] = [abs(a) for a in track['anchors']]
+        track['gt_overlaps'] = [x['gt_overlap'] for x in tubelet['boxes']]
+        track['labels'] = [1 if v >= 0.5 else 0 for v in track['gt_overlaps']]
+        if 'all_scores' in net.blobs.keys():
+            track['all_scores'] = [x['all_score'] for x in tubelet['boxes']]
+        if 'feats' in net.blobs.keys():
+            track['feats'] = [x['feat'] for x in tubelet['boxes']]
+        for blob_name in set(net.blobs.keys()).intersection(set(track.keys())):
+            num_channels = net.blobs[blob_name].shape[1]
+            net.blobs[blob_name].reshape(1, num_channels, 1, track['length'])
+            net.blobs[blob_name].data[...] = np.asarray(track[blob_name], dtype='float32')
+        blobs_out = net.forward()
+        probs = blobs_out['probs'][:, 1, :]
+        for box, prob in zip(tubelet['boxes'], probs.ravel()):
+            box['conv_score'] = float(prob)
+    return new_score_proto

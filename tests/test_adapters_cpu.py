@@ -69,3 +69,12 @@ def test_overlap_merge_top_golden():
 def test_packed_vid_nms_golden():
     G_packed.test_packed_vid_nms_golden()
     G_packed.test_packed_vid_nms_synthetic(5, 77, 4, True)
+
+
+def test_round2_call_sites_golden():
+    """rcnn_sampling_dets_scoring, score_conv_cls (marshalling + TemporalConvNet), threshold/top-k: adapters and the
+    NumPy restatements against what the reference's own functions produced (tests/golden/r02.json)."""
+    G_tub.test_rcnn_sampling_dets_scoring_golden()
+    G_tub.test_score_conv_cls_channel_marshalling_golden()
+    G_tub.test_score_conv_cls_temporal_conv_net_batched()
+    G_tub.test_threshold_topk_pinned_to_fast_rcnn_det_vid()

@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(THREADS) link_frames_kernel(const float4* __re
                                                               int32_t* __restrict__ succ,
                                                               float* __restrict__ best_iou) {
     __shared__ float4 s_box[LINK_STAGE];
-    __shared__ float s_area[LINK_STAGE];
+    __shared__ __align__(8) float s_area[LINK_STAGE];
     const int seg = blockIdx.x;
     const int off = seg_offsets[seg];
     const int n = seg_offsets[seg + 1] - off;
@@ -76,16 +76,42 @@ __global__ void __launch_bounds__(THREADS) link_frames_kernel(const float4* __re
         // barrier + vote: when every box in play is sane (common.cuh) the branch-free division is
         // exact and unions cannot be zero; otherwise the generic IEEE path runs.  Same bits.
         if (__syncthreads_and(ok)) {
+            // sane boxes: two pair IoUs per packed FADD2 / FMUL2 / FFMA2 sequence (common.cuh) -- two of the
+            // thread's rows against one staged box, or (one row per thread) one row against two staged boxes
+            if (ROWS >= 2) {
 #pragma unroll 4
-            for (int j = 0; j < cnt; ++j) {
-                const float4 bj = s_box[j];
-                const float aj = s_area[j];
+                for (int j = 0; j < cnt; ++j) {
+                    const float4 bj = s_box[j];
+                    const float aj = s_area[j];
+                    const f32x2 aj2 = pk2(aj, aj);
 #pragma unroll
-                for (int r = 0; r < ROWS; ++r) {
+                    for (int r = 0; r + 1 < ROWS; r += 2) {
+                        f32x2 inter, uni, nuni;
+                        inter_union_f32x2(bj, aj2, bi[r], bi[r + 1], pk2(ai[r], ai[r + 1]), inter, uni, nuni);
+                        float v0, v1;
+                        upk2(div_sane2(inter, nuni), v0, v1);
+                        if (v0 > best[r]) { best[r] = v0; arg[r] = j0 + j; }      // strict '>' keeps the FIRST maximum
+                        if (v1 > best[r + 1]) { best[r + 1] = v1; arg[r + 1] = j0 + j; }
+                    }
+                }
+            } else {
+                const f32x2 ai2 = pk2(ai[0], ai[0]);
+                int j = 0;
+#pragma unroll 4
+                for (; j + 1 < cnt; j += 2) {
+                    const float2 aj = *reinterpret_cast<const float2*>(s_area + j);
+                    f32x2 inter, uni, nuni;
+                    inter_union_f32x2(bi[0], ai2, s_box[j], s_box[j + 1], pk2(aj.x, aj.y), inter, uni, nuni);
+                    float v0, v1;
+                    upk2(div_sane2(inter, nuni), v0, v1);
+                    if (v0 > best[0]) { best[0] = v0; arg[0] = j0 + j; }
+                    if (v1 > best[0]) { best[0] = v1; arg[0] = j0 + j + 1; }
+                }
+                if (j < cnt) {
                     float inter, uni;
-                    inter_union_f32(bi[r], ai[r], bj, aj, inter, uni);
+                    inter_union_f32(bi[0], ai[0], s_box[j], s_area[j], inter, uni);
                     const float v = div_sane(inter, uni);
-                    if (v > best[r]) { best[r] = v; arg[r] = j0 + j; }      // strict '>' keeps the FIRST maximum
+                    if (v > best[0]) { best[0] = v; arg[0] = j0 + j; }
                 }
             }
         } else {

@@ -124,170 +124,102 @@ template <> struct Vec16<double> { typedef double2 type; static constexpr int V 
 //   leading run  -> r                       (:293-295)
 //   trailing run -> l                       (:296-298)
 //   interior     -> l + (r - l) * (k - i + 1) / (j - i + 1)     (:299-303)
-// Streaming formulation (one read + one write of the row, any row length): rows are cut into
-// 256-element tiles, one warp each.
-//   pass 1 (completion_bounds_kernel): for tiles whose first / last element is missing, the nearest
-//          valid element to the LEFT / RIGHT of the tile (index + value) -- a ballot search that
-//          normally ends in its first 32-element probe -- goes to a small side buffer.  Reading
-//          neighbours in a separate pass keeps the in-place update of pass 2 race-free.
-//   pass 2 (completion_fill_kernel): 16-byte loads, warp max-scan of "last valid index" and min-scan
-//          of "next valid index" (shuffles only, no block barrier), closed form per missing
-//          element, 16-byte stores by the lanes that changed something; tiles without a missing
-//          element return after the load.
-constexpr int CP_ITEMS = 8;                    // elements per lane
-constexpr int CP_TILE = 32 * CP_ITEMS;         // one warp = one 256-element tile
-constexpr int CP_WARPS = 8;                    // tiles per CTA (independent of each other)
+// The update is in place and valid scores never change, so the rows only have to be READ once and
+// the ~5 % missing elements written.  Two kernels, race-free because the first one is the only one
+// that classifies elements, before anything is rewritten:
+//   1. completion_scan_kernel streams the rows (coalesced 4/8-byte loads, 32 in flight per lane) and
+//      writes a "missing" BITMAP, one 32-bit word per 32 elements, straight from warp ballots (lane
+//      stride 1 over the row, so a ballot IS the bitmap word): 1 bit per element of side traffic;
+//   2. completion_fill_kernel reads the bitmap, one thread per word.  A run belongs to the word that
+//      holds its first element (missing bit set, previous bit clear): that thread finds the run's end
+//      in the bitmap alone, loads the two valid neighbours and writes the closed form.  Words without
+//      a run start (84 % on BASELINE's rows) cost one load.
+// Traffic per element: 4 B read + 2 bits of bitmap + ~5 % x (read neighbours, write value), against the
+// 8 B of a read-everything / write-everything pass.
+constexpr int CS_WARPS = 8;                     // warps per CTA of the scan kernel, one 1024-element span each
 
 template <typename T>
-struct TileBounds { int32_t left_idx; int32_t right_idx; T left_val; T right_val; };
-
-// Pass 1: only tiles whose first / last element is missing need a neighbour outside the tile.
-// One THREAD per tile (two loads); the rare tiles that do need a neighbour walk outwards serially.
-template <typename T>
-__global__ void __launch_bounds__(256) completion_bounds_kernel(const T* __restrict__ scores, int64_t L, int64_t ld,
-                                                                const int32_t* __restrict__ lengths,
-                                                                int tiles_per_row, int64_t n_tiles, T miss_thr,
-                                                                TileBounds<T>* __restrict__ bounds) {
-    const int64_t tile_id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tile_id >= n_tiles) return;
-    const int64_t row = tile_id / tiles_per_row;
-    const int tile = (int)(tile_id - row * tiles_per_row);
-    const int len = (int)(lengths ? (int64_t)lengths[row] : L);
-    const int t0 = tile * CP_TILE;
-    if (t0 >= len) return;
-    const int t1 = (t0 + CP_TILE < len) ? t0 + CP_TILE : len;
-    const T* g = scores + row * ld;
-    const bool need_left = g[t0] <= miss_thr, need_right = g[t1 - 1] <= miss_thr;
-    if (!need_left && !need_right) return;
-    TileBounds<T> b;
-    b.left_idx = -1; b.right_idx = len; b.left_val = (T)0; b.right_val = (T)0;
-    if (need_left) {
-        for (int k = t0 - 1; k >= 0; --k) {                     // nearest valid element left of the tile
-            const T v = g[k];
-            if (!(v <= miss_thr)) { b.left_idx = k; b.left_val = v; break; }
+__global__ void __launch_bounds__(CS_WARPS * 32) completion_scan_kernel(const T* __restrict__ scores, int64_t L, int64_t ld,
+                                                                        const int32_t* __restrict__ lengths,
+                                                                        int words_per_row, int spans_per_row,
+                                                                        int64_t n_spans, T miss_thr,
+                                                                        uint32_t* __restrict__ bitmap) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t span = (int64_t)blockIdx.x * CS_WARPS + warp; span < n_spans; span += (int64_t)gridDim.x * CS_WARPS) {
+        const int64_t row = span / spans_per_row;
+        const int sp = (int)(span - row * spans_per_row);
+        const int len = (int)(lengths ? (int64_t)lengths[row] : L);
+        const int e0 = sp * 1024;                               // 32 words of 32 elements
+        const T* g = scores + row * ld;
+        uint32_t mine = 0;                                       // lane j keeps word j of the span
+#pragma unroll
+        for (int jb = 0; jb < 32; jb += 8) {
+            T v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int e = e0 + (jb + q) * 32 + lane;
+                v[q] = e < len ? __ldg(g + e) : (T)0;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int e = e0 + (jb + q) * 32 + lane;
+                const uint32_t word = __ballot_sync(FULL, e < len && v[q] <= miss_thr);
+                if (lane == jb + q) mine = word;
+            }
         }
+        const int w = sp * 32 + lane;
+        if (w < words_per_row) bitmap[row * words_per_row + w] = mine;
     }
-    if (need_right) {
-        for (int k = t1; k < len; ++k) {                        // nearest valid element right of it
-            const T v = g[k];
-            if (!(v <= miss_thr)) { b.right_idx = k; b.right_val = v; break; }
-        }
-    }
-    bounds[tile_id] = b;
 }
 
-// Pass 2: persistent warps, one 256-element tile at a time, no block barrier.  Lanes load 8
-// consecutive elements (16-byte loads) and publish them plus an 8-bit validity mask in the warp's
-// shared scratch.  The tile's MISSING elements are then dealt out evenly over the lanes (ballots per
-// position + __fns pick the m-th one): missing elements are ~5 % of a row, so one pass of the closed
-// form serves the whole tile -- walking each lane's own 8 positions instead would make every warp
-// execute the divergent body 8 times (first version: 489 instructions per tile).  Last / next valid
-// index come from the 256-bit validity set, values from the scratch or the tile's boundary record.
 template <typename T>
-__global__ void __launch_bounds__(CP_WARPS * 32) completion_fill_kernel(T* __restrict__ scores, int64_t L, int64_t ld,
-                                                                        const int32_t* __restrict__ lengths,
-                                                                        int tiles_per_row, int64_t n_tiles, T miss_thr,
-                                                                        int vec_ok,
-                                                                        const TileBounds<T>* __restrict__ bounds,
-                                                                        uint32_t* status) {
-    __shared__ __align__(16) T s_val_all[CP_WARPS][CP_TILE];
-    __shared__ __align__(16) uint32_t s_ok_all[CP_WARPS][8];      // 256 validity bits per tile
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    T* s_val = s_val_all[warp];
-    uint32_t* s_ok = s_ok_all[warp];
-    constexpr int V = 16 / sizeof(T);
-    for (int64_t tile_id = (int64_t)blockIdx.x * CP_WARPS + warp; tile_id < n_tiles;
-         tile_id += (int64_t)gridDim.x * CP_WARPS) {
-        const int64_t row = tile_id / tiles_per_row;
-        const int tile = (int)(tile_id - row * tiles_per_row);
-        const int len = (int)(lengths ? (int64_t)lengths[row] : L);
-        const int t0 = tile * CP_TILE;
-        if (t0 >= len) continue;
-        T* g = scores + row * ld;
-        const int e0 = t0 + lane * CP_ITEMS;                   // this lane's 8 consecutive elements
-        __align__(16) T v[CP_ITEMS];
-        if (vec_ok && e0 + CP_ITEMS <= len) {
-#pragma unroll
-            for (int q = 0; q < CP_ITEMS; q += V)
-                *reinterpret_cast<typename Vec16<T>::type*>(v + q) =
-                    *reinterpret_cast<const typename Vec16<T>::type*>(g + e0 + q);
-        } else {
-#pragma unroll
-            for (int q = 0; q < CP_ITEMS; ++q) v[q] = (e0 + q < len) ? g[e0 + q] : (T)0;
-        }
-        unsigned okm = 0, missm = 0;                           // bit q: element q valid / missing
-#pragma unroll
-        for (int q = 0; q < CP_ITEMS; ++q) {
-            const bool in = e0 + q < len;
-            const bool miss = v[q] <= miss_thr;
-            if (in && !miss) okm |= 1u << q;
-            if (in && miss) missm |= 1u << q;
-        }
-        if (!__any_sync(FULL, missm != 0)) continue;           // nothing to fill in this tile
-        __syncwarp();                                          // previous tile's readers are done
-#pragma unroll
-        for (int q = 0; q < CP_ITEMS; q += V)
-            *reinterpret_cast<typename Vec16<T>::type*>(s_val + lane * CP_ITEMS + q) =
-                *reinterpret_cast<const typename Vec16<T>::type*>(v + q);
-        reinterpret_cast<uint8_t*>(s_ok)[lane] = (uint8_t)okm;
-        // where are the missing elements?  cq[q] = lanes whose element q is missing
-        unsigned cq[CP_ITEMS];
-        int total = 0;
-#pragma unroll
-        for (int q = 0; q < CP_ITEMS; ++q) {
-            cq[q] = __ballot_sync(FULL, (missm >> q) & 1u);
-            total += __popc(cq[q]);
-        }
-        __syncwarp();
-        const uint4 w_lo = *reinterpret_cast<const uint4*>(s_ok), w_hi = *reinterpret_cast<const uint4*>(s_ok + 4);
-        const uint32_t okw[8] = {w_lo.x, w_lo.y, w_lo.z, w_lo.w, w_hi.x, w_hi.y, w_hi.z, w_hi.w};
-        for (int m = lane; m < total; m += 32) {
-            // the m-th missing element (position-major order): position q, then the lane owning it
-            int q = 0, rest = m;
-#pragma unroll
-            for (int qq = 0; qq < CP_ITEMS - 1; ++qq) {
-                const int c = __popc(cq[qq]);
-                if (q == qq && rest >= c) { rest -= c; q = qq + 1; }
-            }
-            unsigned sel = cq[0];
-#pragma unroll
-            for (int qq = 1; qq < CP_ITEMS; ++qq) sel = (q == qq) ? cq[qq] : sel;
-            const int src = __fns(sel, 0, rest + 1);           // lane that owns it
-            const int e = src * CP_ITEMS + q;                  // element index inside the tile
-            const int k = t0 + e;
-            // last valid element before e / first valid element after e, inside the tile
-            int lv = -1, nv = 0x7fffffff;
-#pragma unroll
-            for (int w = 7; w >= 0; --w) {
-                unsigned mword = okw[w];
-                if (w == (e >> 5)) mword &= (1u << (e & 31)) - 1u;
-                if (w <= (e >> 5) && lv < 0 && mword) lv = w * 32 + 31 - __clz(mword);
-            }
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                unsigned mword = okw[w];
-                if (w == (e >> 5)) mword &= ~((2u << (e & 31)) - 1u);
-                if (w >= (e >> 5) && nv == 0x7fffffff && mword) nv = w * 32 + __ffs(mword) - 1;
-            }
-            int i, j;             // run = [i, j) in row coordinates
-            T lft, rgt;
-            TileBounds<T> b;
-            b.left_idx = -1; b.right_idx = len; b.left_val = (T)0; b.right_val = (T)0;
-            if (lv < 0 || nv == 0x7fffffff) b = bounds[tile_id];   // a run that touches the tile edge
-            if (lv >= 0) { i = t0 + lv + 1; lft = s_val[lv]; }
-            else { i = b.left_idx + 1; lft = b.left_val; }
-            if (nv != 0x7fffffff) { j = t0 + nv; rgt = s_val[nv]; }
-            else { j = b.right_idx; rgt = b.right_val; }
-            T r;
-            if (i == 0) {
-                if (j >= len) { if (k == 0) atomicOr(status, VDET_STATUS_ALL_MISSING); continue; }
-                r = rgt;
-            } else if (j >= len) {
-                r = lft;
+__global__ void __launch_bounds__(256) completion_fill_kernel(T* __restrict__ scores, int64_t L, int64_t ld,
+                                                              const int32_t* __restrict__ lengths,
+                                                              int words_per_row, int64_t n_words,
+                                                              const uint32_t* __restrict__ bitmap,
+                                                              uint32_t* status) {
+    const int64_t wid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (wid >= n_words) return;
+    const uint32_t word = __ldg(bitmap + wid);
+    if (word == 0u) return;
+    const int64_t row = wid / words_per_row;
+    const int wi = (int)(wid - row * words_per_row);
+    const uint32_t carry = wi > 0 ? (__ldg(bitmap + wid - 1) >> 31) : 0u;
+    uint32_t starts = word & ~((word << 1) | carry);            // missing, and the element before it is not
+    if (starts == 0u) return;
+    const int len = (int)(lengths ? (int64_t)lengths[row] : L);
+    const uint32_t* brow = bitmap + row * words_per_row;
+    T* g = scores + row * ld;
+    while (starts) {
+        const int sbit = __ffs(starts) - 1;
+        starts &= starts - 1;
+        const int i = wi * 32 + sbit;                            // run = [i, j)
+        // end of the run: first clear bit at or after i (bits beyond the row are clear)
+        int j;
+        {
+            uint32_t rest = ~word & ~((2u << sbit) - 1u);        // clear bits above sbit in this word
+            if (sbit == 31) rest = 0u;
+            if (rest) {
+                j = wi * 32 + __ffs(rest) - 1;
             } else {
-                r = t_add(lft, t_div(t_mul(t_sub(rgt, lft), (T)(k - i + 1)), (T)(j - i + 1)));
+                int w2 = wi + 1;
+                uint32_t inv = 0u;
+                while (w2 < words_per_row && (inv = ~__ldg(brow + w2)) == 0u) ++w2;
+                j = (w2 < words_per_row) ? w2 * 32 + __ffs(inv) - 1 : len;
             }
-            g[k] = r;
+            if (j > len) j = len;
+        }
+        if (i == 0) {
+            if (j >= len) { atomicOr(status, VDET_STATUS_ALL_MISSING); continue; }     // tubelet_cls.py:295 IndexError
+            const T r = g[j];
+            for (int k = i; k < j; ++k) g[k] = r;
+        } else if (j >= len) {
+            const T l = g[i - 1];
+            for (int k = i; k < j; ++k) g[k] = l;
+        } else {
+            const T l = g[i - 1], r = g[j];
+            const T d = t_sub(r, l), den = (T)(j - i + 1);
+            for (int k = i; k < j; ++k) g[k] = t_add(l, t_div(t_mul(d, (T)(k - i + 1)), den));
         }
     }
 }
@@ -447,27 +379,32 @@ static int run_conv(const void* in, void* out, int64_t n_rows, int64_t L, int64_
     return VDET_OK;
 }
 
+static inline size_t completion_bitmap_words(int64_t n_rows, int64_t L) {
+    return (size_t)(n_rows > 0 ? n_rows : 0) * (size_t)((L + 31) / 32);
+}
+
 template <typename T>
 static int run_completion(void* scores, int64_t n_rows, int64_t L, int64_t ld, const int32_t* lengths,
                           double miss_thr, uint32_t* status, void* ws, size_t ws_bytes, cudaStream_t st) {
-    const int64_t tiles = (L + CP_TILE - 1) / CP_TILE;
-    const int64_t n_tiles = tiles * n_rows;
-    if (n_tiles > 0x7fffffff || L >= 0x7fffffff) { set_error("score_completion: too large"); return VDET_ERR_UNSUPPORTED; }
-    const size_t need = (size_t)n_tiles * sizeof(TileBounds<T>);
+    if (L >= 0x7fffffff - 1024) { set_error("score_completion: too large"); return VDET_ERR_UNSUPPORTED; }
+    const int words_per_row = (int)((L + 31) / 32);
+    const int spans_per_row = (words_per_row + 31) / 32;
+    const int64_t n_words = (int64_t)words_per_row * n_rows;
+    const int64_t n_spans = (int64_t)spans_per_row * n_rows;
+    const size_t need = (size_t)n_words * sizeof(uint32_t);
     if (ws == nullptr || ws_bytes < need) {
         set_error("score_completion: workspace of %zu bytes needed", need);
         return VDET_ERR_WORKSPACE;
     }
-    TileBounds<T>* bounds = (TileBounds<T>*)ws;
-    completion_bounds_kernel<T><<<(unsigned)((n_tiles + 255) / 256), 256, 0, st>>>((const T*)scores, L, ld, lengths,
-                                                                              (int)tiles, n_tiles, (T)miss_thr, bounds);
+    uint32_t* bitmap = (uint32_t*)ws;
+    int64_t grid = (n_spans + CS_WARPS - 1) / CS_WARPS;
+    const int64_t cap = (int64_t)sm_count_cached() * 8;                // 8 resident CTAs per SM, persistent
+    if (grid > cap) grid = cap;
+    completion_scan_kernel<T><<<(unsigned)grid, CS_WARPS * 32, 0, st>>>((const T*)scores, L, ld, lengths, words_per_row,
+                                                                        spans_per_row, n_spans, (T)miss_thr, bitmap);
     VDET_LAUNCH_CHECK();
-    const int vec_ok = (((uintptr_t)scores & 15) == 0 && (ld % (16 / sizeof(T))) == 0) ? 1 : 0;
-    int64_t fill_grid = (n_tiles + CP_WARPS - 1) / CP_WARPS;
-    const int64_t fill_cap = (int64_t)sm_count_cached() * 8;          // 8 resident CTAs per SM
-    if (fill_grid > fill_cap) fill_grid = fill_cap;
-    completion_fill_kernel<T><<<(unsigned)fill_grid, CP_WARPS * 32, 0, st>>>(
-        (T*)scores, L, ld, lengths, (int)tiles, n_tiles, (T)miss_thr, vec_ok, bounds, status);
+    completion_fill_kernel<T><<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>((T*)scores, L, ld, lengths, words_per_row,
+                                                                                 n_words, bitmap, status);
     VDET_LAUNCH_CHECK();
     return VDET_OK;
 }
@@ -477,9 +414,8 @@ static int run_completion(void* scores, int64_t n_rows, int64_t L, int64_t ld, c
 using namespace vdet;
 
 extern "C" size_t vdet_score_completion_workspace_bytes(int64_t n_rows, int64_t L, int dtype) {
-    const int64_t tiles = (L + CP_TILE - 1) / CP_TILE;
-    const size_t rec = dtype == VDET_DTYPE_F64 ? sizeof(TileBounds<double>) : sizeof(TileBounds<float>);
-    return (size_t)(tiles * (n_rows > 0 ? n_rows : 0)) * rec + 256;
+    (void)dtype;
+    return completion_bitmap_words(n_rows, L) * sizeof(uint32_t) + 256;      // the "missing" bitmap
 }
 
 extern "C" int vdet_score_completion(void* scores, int dtype, int64_t n_rows, int64_t L, int64_t ld,

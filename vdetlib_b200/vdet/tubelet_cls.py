@@ -118,53 +118,130 @@ def _maxpool_rows(tubelets, rows, window_size):
             b['det_score'] = float(v)
 
 
+class _Blob(object):
+    """The two things score_conv_cls touches on a Caffe blob: ``shape`` / ``reshape`` and ``data``."""
+
+    def __init__(self, channels):
+        self.data = np.zeros((1, channels, 1, 1), dtype=np.float32)
+
+    @property
+    def shape(self):
+        return self.data.shape
+
+    def reshape(self, *shape):
+        if tuple(shape) != self.data.shape:
+            self.data = np.zeros(shape, dtype=np.float32)
+
+
+CONV_CHANNELS = ('det_scores', 'track_scores', 'anchors', 'abs_anchors', 'gt_overlaps', 'labels', 'all_scores', 'feats')
+
+
 class TemporalConvNet(object):
     """Stand-in for the Caffe net of ``score_conv_cls`` (vdet/tubelet_cls.py:15-51).
 
-    The reference feeds per-tubelet 1-D channels to an external Caffe model whose prototxt and
-    weights are not part of vdetlib (parity unpinned).  Here the "net" is an explicit
-    depthwise temporal filter: ``taps[name]`` is an odd-length 1-D filter for channel ``name``
-    (one of det_scores / track_scores / anchors / abs_anchors / gt_overlaps), the per-channel
-    responses are summed, plus ``bias``.
+    The reference feeds per-tubelet 1-D channels as ``(1, C, 1, L)`` blobs to an external Caffe model whose
+    prototxt and weights are not part of vdetlib (the arithmetic is **parity unpinned**).  What IS
+    pinned by the reference is the marshalling -- which channels exist, how they are computed from the score
+    proto, their blob shapes, and that ``probs[:, 1, :]`` becomes ``conv_score`` -- and this class offers
+    exactly that surface: ``blobs`` (name -> blob with ``shape`` / ``reshape`` / ``data``), ``forward()``
+    returning ``{'probs': (1, 2, 1, L)}``.  The model behind it is explicit: ``taps[name]`` is an odd-length
+    temporal filter per channel of blob ``name`` ([w] or [C, w]); the depthwise responses (one launch of
+    ``vdet_temporal_conv1d`` over all channels) are summed with ``bias`` into a logit z per frame and
+    ``probs = softmax([0, z])``, i.e. ``probs[:, 1] = 1 / (1 + exp(-z))``.
     """
 
     def __init__(self, taps, bias=0.0, pad_mode="zero"):
-        self.taps = {k: np.asarray(v, dtype=np.float64) for k, v in taps.items()}
+        self.taps = {}
+        for k, v in taps.items():
+            if k not in CONV_CHANNELS:
+                raise KeyError(k)
+            self.taps[k] = np.atleast_2d(np.asarray(v, dtype=np.float32))      # [C, w]
         self.bias = float(bias)
         self.pad_mode = pad_mode
+        self.blobs = {k: _Blob(v.shape[0]) for k, v in self.taps.items()}
+
+    def logits(self, rows, lengths=None):
+        """rows: dict name -> float32 CUDA tensor [R * C_name, Lmax] (R tubelets, channel-minor); returns z [R, Lmax]."""
+        z = None
+        for name, taps in self.taps.items():
+            x = rows[name]
+            C = taps.shape[0]
+            lens = None if lengths is None else lengths.repeat_interleave(C)
+            y = ops.temporal_conv1d(x, torch.from_numpy(taps).to(x.device), self.pad_mode, lens)
+            y = y.view(-1, C, x.shape[1]).sum(dim=1)
+            z = y if z is None else z + y
+        return z + self.bias
+
+    def forward(self):
+        """Caffe's ``net.forward()`` for the blobs as they are now (one tubelet)."""
+        dev = ops.default_device()
+        rows = {k: torch.from_numpy(np.ascontiguousarray(b.data[0, :, 0, :])).to(dev) for k, b in self.blobs.items()}
+        z = self.logits(rows).cpu().numpy().astype(np.float32)[0]
+        p1 = (1.0 / (1.0 + np.exp(-z.astype(np.float64)))).astype(np.float32)
+        return {'probs': np.stack([1.0 - p1, p1]).reshape(1, 2, 1, -1)}
+
+
+def _conv_channels(tubelet, blob_names):
+    """The per-tubelet channel dict of vdet/tubelet_cls.py:19-41."""
+    track = {}
+    boxes = tubelet['boxes']
+    track['length'] = len(boxes)
+    track['gt'] = tubelet['gt']
+    track['mean_iou'] = np.mean([[x['gt_overlap'] for x in boxes]])
+    track['det_scores'] = [x['det_score'] for x in boxes]
+    track['track_scores'] = [x['track_score'] for x in boxes]
+    track['anchors'] = [x['anchor'] * 1. / track['length'] for x in boxes]         # :28
+    track['abs_anchors'] = [abs(a) for a in track['anchors']]                       # :30
+    track['gt_overlaps'] = [x['gt_overlap'] for x in boxes]
+    track['labels'] = [1 if iou >= 0.5 else 0 for iou in track['gt_overlaps']]      # :33
+    # skip memory heavy features if possible
+    if 'all_scores' in blob_names:
+        track['all_scores'] = [x['all_score'] for x in boxes]
+    if 'feats' in blob_names:
+        track['feats'] = [x['feat'] for x in boxes]
+    return track
 
 
 def score_conv_cls(score_proto, net):
-    """Temporal-convolution rescoring: writes ``conv_score`` per box.  vdet/tubelet_cls.py:15-51
-    with ``net`` a :class:`TemporalConvNet`."""
+    """Temporal-convolution rescoring: writes ``conv_score`` per box.  vdet/tubelet_cls.py:15-51.
+
+    ``net`` is anything with Caffe's surface (``blobs[name].shape / reshape / data``, ``forward()`` returning
+    ``probs``) -- a real Caffe net works unchanged, one forward per tubelet like the reference.  With a
+    :class:`TemporalConvNet` all tubelets are evaluated in ONE batch on the GPU (ragged rows): same channels,
+    same result as its own per-tubelet ``forward()``."""
     new_score_proto = copy.copy(score_proto)
-    tubelets = [t for t in new_score_proto['tubelets'] if len(t['boxes'])]
-    if not tubelets:
+    blob_names = set(net.blobs.keys())
+    if isinstance(net, TemporalConvNet) and all(len(t['boxes']) for t in new_score_proto['tubelets']) \
+            and new_score_proto['tubelets']:
+        tubelets = new_score_proto['tubelets']
+        tracks = [_conv_channels(t, blob_names) for t in tubelets]
+        lens = np.asarray([tr['length'] for tr in tracks], dtype=np.int32)
+        Lmax = int(lens.max())
+        dev = ops.default_device()
+        rows = {}
+        for name in blob_names.intersection(tracks[0].keys()):
+            C = net.blobs[name].shape[1]
+            buf = np.zeros((len(tracks), C, Lmax), dtype=np.float32)
+            for k, tr in enumerate(tracks):
+                buf[k, :, :lens[k]] = np.asarray(tr[name], dtype='float32').reshape(lens[k], -1).T if C > 1 \
+                    else np.asarray(tr[name], dtype='float32')
+            rows[name] = torch.from_numpy(buf.reshape(-1, Lmax)).to(dev)
+        z = net.logits(rows, torch.from_numpy(lens).to(dev)).cpu().numpy().astype(np.float32)
+        p1 = (1.0 / (1.0 + np.exp(-z.astype(np.float64)))).astype(np.float32)
+        for t, row in zip(tubelets, p1):
+            for box, prob in zip(t['boxes'], row):
+                box['conv_score'] = float(prob)
         return new_score_proto
-    total = None
-    for name, taps in net.taps.items():
-        rows = []
-        for t in tubelets:
-            length = len(t['boxes'])
-            if name == 'det_scores':
-                rows.append([b['det_score'] for b in t['boxes']])
-            elif name == 'track_scores':
-                rows.append([b['track_score'] for b in t['boxes']])
-            elif name == 'anchors':
-                rows.append([b['anchor'] * 1. / length for b in t['boxes']])        # :28
-            elif name == 'abs_anchors':
-                rows.append([abs(b['anchor'] * 1. / length) for b in t['boxes']])   # :30
-            elif name == 'gt_overlaps':
-                rows.append([b['gt_overlap'] for b in t['boxes']])
-            else:
-                raise KeyError(name)
-        dev, lens_dev, lens = _pack_rows(rows)
-        y = ops.temporal_conv1d(dev, torch.from_numpy(taps.reshape(1, -1)).to(dev.device), net.pad_mode, lens_dev)
-        total = y if total is None else total + y
-    out = (total + net.bias).cpu().numpy()
-    for t, row in zip(tubelets, out):
-        for b, v in zip(t['boxes'], row):
-            b['conv_score'] = float(v)
+    for tubelet in new_score_proto['tubelets']:
+        track = _conv_channels(tubelet, blob_names)
+        for blob_name in blob_names.intersection(set(track.keys())):
+            num_channels = net.blobs[blob_name].shape[1]
+            net.blobs[blob_name].reshape(1, num_channels, 1, track['length'])                  # :43-45
+            net.blobs[blob_name].data[...] = np.asarray(track[blob_name], dtype='float32')      # :46
+        blobs_out = net.forward()
+        probs = blobs_out['probs'][:, 1, :]                                                     # :48
+        for box, prob in zip(tubelet['boxes'], probs.ravel()):
+            box['conv_score'] = float(prob)
     return new_score_proto
 
 
@@ -244,6 +321,84 @@ def raw_dets_spatial_max_pooling(vid_proto, track_proto, frame_to_det, class_idx
     score_proto['tubelets'] = tubelets_proto
     do_score_completion(score_proto)
     return score_proto
+
+
+def rcnn_sampling_dets_scoring(vid_proto, track_proto, det_proto, net, class_idx, rcnn_model, overlap_thres=0.7,
+                               save_feat=False, save_all_sc=False, score_column=None):
+    """Score tubelet boxes with a CNN + SVM and let overlapping detections out-score them.
+    vdet/tubelet_cls.py:196-260, same positional arguments.
+
+    The CNN / SVM are out of scope (Caffe + images); they enter as callables with the meaning of the
+    reference's calls: ``net(frame_path, boxes) -> features [P, F]`` stands for
+    ``googlenet_features(imread(frame_path), boxes, net, 'pool5')`` (:213, :241) and
+    ``rcnn_model(features) -> scores [P, K]`` for ``svm_scores(features, svm_from_rcnn_model(rcnn_model))``
+    (:198, :214).  ``score_column``: the column of ``scores`` that holds ``class_idx``
+    (reference: ``index_vdet_to_det[class_idx] - 1`` of a 200-column DET model, :215-218).
+
+    The pooling epilogue (:221-247) is one batched launch for the whole video: per tubelet box the detections of
+    its frame with IoU > ``overlap_thres`` (strict), FIRST arg-max of their class score (``det_score``, i.e.
+    looked up by class_index), ``-inf`` when none; the detection replaces score and bbox only if its score is
+    strictly greater than the box's own CNN score."""
+    tubelets_proto = tubelets_proto_from_tracks_proto(track_proto['tracks'], class_idx)
+    logging.info("Scoring {} for {}...".format(vid_proto['video'], imagenet_vdet_classes[class_idx]))
+    if score_column is None:
+        raise ValueError("rcnn_sampling_dets_scoring: score_column (the SVM column of class_idx) is required")
+    frame_to_det_idx = defaultdict(list)
+    dets = det_proto['detections']
+    for i, det in enumerate(dets):
+        frame_to_det_idx[det['frame']].append(i)
+    by_frame = defaultdict(list)
+    for i, tubelet in enumerate(tubelets_proto):
+        seen = set()
+        for j, box in enumerate(tubelet['boxes']):
+            if box['frame'] not in seen:                       # tubelet_box_at_frame: the FIRST box of that frame
+                seen.add(box['frame'])
+                by_frame[box['frame']].append((i, j))
+    tub_boxes, tub_frames, where, own = [], [], [], []
+    frame_dets = {}
+    for frame in vid_proto['frames']:
+        fid = frame['frame']
+        entries = by_frame.get(fid, [])
+        if not entries:
+            continue
+        path = str(vid_proto['root_path'] + '/' + frame['path']) if 'root_path' in vid_proto else frame['path']
+        valid_boxes = np.asarray([tubelets_proto[i]['boxes'][j]['bbox'] for i, j in entries])
+        features = net(path, valid_boxes)
+        scores = np.asarray(rcnn_model(features))
+        cls_scores = scores[:, score_column]
+        idx = frame_to_det_idx.get(fid, [])
+        if idx:
+            from ..utils.protocol import det_score
+            frame_dets[fid] = (np.asarray([dets[k]['bbox'] for k in idx]),
+                               np.asarray([det_score(dets[k], class_idx) for k in idx]))
+        for (i, j), sc, feat, all_sc in zip(entries, cls_scores, features, scores):
+            tub_boxes.append(tubelets_proto[i]['boxes'][j]['bbox'])
+            tub_frames.append(fid)
+            where.append((i, j))
+            own.append((sc, feat, all_sc, path))
+    if not where:
+        return tubelets_proto
+    arg, score = _pool_on_gpu(tub_boxes, tub_frames, frame_dets, overlap_thres, _lib.POOL_ARGMAX_SCORE)
+    for (i, j), fid, a, s, (sc, feat, all_sc, path) in zip(where, tub_frames, arg, score, own):
+        cur = tubelets_proto[i]['boxes'][j]
+        max_score = frame_dets[fid][1][a] if a >= 0 else -np.inf        # :236-238
+        if max_score > sc:                                                # :239
+            max_box = frame_dets[fid][0][a].tolist()
+            cur['det_score'] = max_score
+            cur['bbox'] = max_box
+            if save_feat or save_all_sc:
+                max_feat = net(path, [max_box])
+                if save_feat:
+                    cur['feat'] = np.asarray(max_feat).ravel().tolist()
+                if save_all_sc:
+                    cur['all_score'] = np.asarray(rcnn_model(max_feat)).ravel().tolist()
+        else:
+            cur['det_score'] = sc
+            if save_feat:
+                cur['feat'] = np.asarray(feat).ravel().tolist()
+            if save_all_sc:
+                cur['all_score'] = np.asarray(all_sc).ravel().tolist()
+    return tubelets_proto
 
 
 def anchor_propagate(vid_proto, track_proto, det_proto, class_idx):
