@@ -150,13 +150,10 @@ def test_score_proto_functions():
     bad = {'video': 'v', 'method': 'm', 'tubelets': [{'gt': 0, 'boxes': [{'det_score': -1e5}, {'det_score': -1e5}]}]}
     with pytest.raises(IndexError):
         tubelet_cls.do_score_completion(bad)
-    # temporal convolution stand-in: equals the NumPy restatement
-    net = tubelet_cls.TemporalConvNet({'det_scores': [0.25, 0.5, 0.25]}, bias=0.1)
-    out = tubelet_cls.score_conv_cls(copy.deepcopy(sp), net)
-    for t_in, t_out in zip(sp['tubelets'], out['tubelets']):
-        x = np.asarray([[b['det_score'] for b in t_in['boxes']]])
-        want = oracle_np.temporal_conv1d(x, np.asarray([[0.25, 0.5, 0.25]])) + 0.1
-        assert np.array_equal(np.asarray([b['conv_score'] for b in t_out['boxes']]), want[0])
+    # score_conv_cls reads gt_overlap / track_score of every box like the reference (:21-32): a proto without them
+    # fails the same way (the conv itself: test_score_conv_cls_* below)
+    with pytest.raises(KeyError):
+        tubelet_cls.score_conv_cls(copy.deepcopy(sp), tubelet_cls.TemporalConvNet({'det_scores': [0.25, 0.5, 0.25]}))
 
 
 def test_vid_nms_and_image_nms_protos_golden():
@@ -183,6 +180,26 @@ def test_greedy_tracking_golden():
     opts = helpers.Opts(max_tracks=4, thres=0.6, nms_thres=None)
     tp = track.greedily_track_from_raw_dets(vid, det_info, helpers.fake_tracker, 3, opts)
     assert tp == out["greedy_raw"]
+    # the reference's restart-and-retry around the tracker call (vdet/track.py:159-168) as a hook: a tracker that
+    # fails once per anchor is retried after opts.on_tracker_error ran; without the hook the error propagates
+    calls = {"fail": 0, "hook": 0}
+
+    def flaky(vid_proto, frame_id, bbox, o):
+        if not getattr(o, "restarted", False):
+            calls["fail"] += 1
+            raise RuntimeError("tracker backend died")
+        o.restarted = False
+        return helpers.fake_tracker(vid_proto, frame_id, bbox, o)
+    flaky.__name__ = "fake_tracker"
+
+    def hook(o):
+        calls["hook"] += 1
+        o.restarted = True
+    opts = helpers.Opts(max_tracks=4, thres=0.6, nms_thres=None, on_tracker_error=hook)
+    assert track.greedily_track_from_raw_dets(vid, det_info, flaky, 3, opts) == out["greedy_raw"]
+    assert calls["hook"] == calls["fail"] == len(out["greedy_raw"]["tracks"])
+    with pytest.raises(RuntimeError):
+        track.greedily_track_from_raw_dets(vid, det_info, flaky, 3, helpers.Opts(max_tracks=4, thres=0.6, nms_thres=None))
 
 
 def test_greedy_tracking_keep_state_vs_oracle():
@@ -218,6 +235,10 @@ def test_score_proto_interpolation_golden():
     got = tubelet_cls.score_proto_interpolation(sp_in, p["interp_vid"])
     assert got == p["out"]["interp"]
     assert sp_in == p["interp_in"]                                   # input untouched
+    dup = copy.deepcopy(p["interp_in"])
+    dup['tubelets'][0]['boxes'].append(copy.deepcopy(dup['tubelets'][0]['boxes'][0]))
+    with pytest.raises(ValueError):
+        tubelet_cls.score_proto_interpolation(dup, p["interp_vid"])      # two boxes on one frame: refused
     spg = copy.deepcopy(p["interp_in"]); spg['tubelets'][1]['gt'] = 1
     with pytest.raises(ValueError):
         tubelet_cls.score_proto_interpolation(spg, p["interp_vid"])
@@ -339,18 +360,9 @@ def test_score_conv_cls_temporal_conv_net_batched():
     class Wrapped(object):
         def __init__(self, n):
             self.blobs, self.forward = n.blobs, n.forward
-    single_sp = copy.deepcopy(sp0)
-    for t in single_sp['tubelets']:                                # all_scores as [C][L] rows for the (1, C, 1, L) blob
-        L = len(t['boxes'])
-    single = None
-    try:
-        single = tubelet_cls.score_conv_cls(single_sp, Wrapped(tubelet_cls.TemporalConvNet(
-            {k: v for k, v in taps.items() if k != "all_scores"}, bias=-0.3)))
-    except ValueError:
-        pass
-    net2 = tubelet_cls.TemporalConvNet({k: v for k, v in taps.items() if k != "all_scores"}, bias=-0.3)
-    batched2 = tubelet_cls.score_conv_cls(copy.deepcopy(sp0), net2)
-    assert single is not None
+    one_d = {k: v for k, v in taps.items() if k != "all_scores"}       # (the reference's own [L, C] -> (1, C, 1, L) assignment
+    single = tubelet_cls.score_conv_cls(copy.deepcopy(sp0), Wrapped(tubelet_cls.TemporalConvNet(one_d, bias=-0.3)))   # only broadcasts for C == 1)
+    batched2 = tubelet_cls.score_conv_cls(copy.deepcopy(sp0), tubelet_cls.TemporalConvNet(one_d, bias=-0.3))
     a = np.concatenate([[b['conv_score'] for b in t['boxes']] for t in single['tubelets']])
     b2 = np.concatenate([[b['conv_score'] for b in t['boxes']] for t in batched2['tubelets']])
     assert np.allclose(a, b2, rtol=0, atol=1e-6)

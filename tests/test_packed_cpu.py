@@ -148,6 +148,14 @@ def test_proto_load_dump_take_the_packed_path(tmp_path):
     assert protocol.proto_load(j)["video"] == "json version"
     protocol.proto_dump(det, j + ".vdetpk")
     assert _same(protocol.proto_load(j), det)
+    # ... but only while it is not older than the file it stands for (a regenerated JSON must win)
+    import os
+    import time
+    st = os.stat(j + ".vdetpk")
+    os.utime(j, (st.st_atime, st.st_mtime + 5))
+    assert protocol.proto_load(j)["video"] == "json version"
+    os.utime(j + ".vdetpk", (time.time() + 10, time.time() + 10))
+    assert _same(protocol.proto_load(j), det)
     # and the reference formats still work
     protocol.proto_dump(det, str(tmp_path / "y.det.gz"))
     assert _same(protocol.proto_load(str(tmp_path / "y.det")), det)

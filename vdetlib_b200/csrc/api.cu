@@ -5,9 +5,14 @@
 
 #include "common.cuh"
 #include <emmintrin.h>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <cstring>
+#include <mutex>
 #include <thread>
 #include <vector>
+#include <unistd.h>
 
 namespace vdet {
 
@@ -95,6 +100,93 @@ void copy_stream_range(unsigned char* d, const unsigned char* s, size_t bytes) {
     _mm_sfence();
 }
 
+// ---- persistent staging threads -----------------------------------------------------------------
+// The end-to-end path stages a 41 MB shard per step (~1 ms): starting and joining 7 threads per call costs a
+// visible fraction of that, so the copy ranges go to a small pool of persistent workers.  A worker that runs
+// out of work keeps polling for ~200 us (the next step's copy usually arrives within that) before it sleeps on
+// a condition variable; the calling thread takes ranges too.  After a fork() the child starts a fresh pool.
+struct CopyJob { unsigned char* d; const unsigned char* s; size_t n; };
+
+namespace {
+struct CopyPool {
+    // One batch of ranges per call.  `state` = (generation << 32) | next range index: a worker claims a range with
+    // a compare-and-swap on the whole word, so a claim can only succeed while ITS generation is the active one --
+    // and then the batch fields it read (published before the state word) are that generation's.
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<std::thread> workers;
+    std::atomic<const CopyJob*> jobs{nullptr};
+    std::atomic<uint32_t> n_jobs{0};
+    std::atomic<uint32_t> done{0};
+    std::atomic<uint64_t> state{0};
+    std::atomic<bool> stop{false};
+    pid_t owner = 0;
+
+    bool claim_and_copy() {                            // false: nothing left in the active batch
+        for (;;) {
+            const uint64_t s = state.load(std::memory_order_acquire);
+            const uint32_t idx = (uint32_t)s;
+            const CopyJob* js = jobs.load(std::memory_order_acquire);
+            const uint32_t n = n_jobs.load(std::memory_order_acquire);
+            if (idx >= n) return false;
+            uint64_t expect = s;
+            if (!state.compare_exchange_weak(expect, s + 1, std::memory_order_acq_rel)) continue;
+            const CopyJob j = js[idx];
+            copy_stream_range(j.d, j.s, j.n);
+            done.fetch_add(1, std::memory_order_acq_rel);
+        }
+    }
+    void worker() {
+        uint64_t seen_gen = state.load(std::memory_order_acquire) >> 32;
+        for (;;) {
+            bool got = false;
+            const auto t0 = std::chrono::steady_clock::now();
+            while (std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(200)) {     // poll, then sleep
+                if (stop.load(std::memory_order_relaxed)) return;
+                if ((state.load(std::memory_order_acquire) >> 32) != seen_gen) { got = true; break; }
+                _mm_pause();
+            }
+            if (!got) {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop.load() || (state.load(std::memory_order_acquire) >> 32) != seen_gen; });
+                if (stop.load()) return;
+            }
+            seen_gen = state.load(std::memory_order_acquire) >> 32;
+            while (claim_and_copy()) {}
+        }
+    }
+    void ensure(int n_workers) {
+        if (owner != getpid()) {                       // first use (a forked child gets a fresh pool object, see below)
+            workers.clear();
+            owner = getpid();
+        }
+        while ((int)workers.size() < n_workers) workers.emplace_back([this] { worker(); });
+    }
+    void run(const std::vector<CopyJob>& js) {
+        ensure((int)js.size() - 1);
+        const uint64_t gen = (state.load(std::memory_order_acquire) >> 32) + 1;
+        {
+            std::lock_guard<std::mutex> lk(mu);        // the state word changes under the lock sleepers wait with
+            done.store(0, std::memory_order_relaxed);
+            jobs.store(js.data(), std::memory_order_release);
+            n_jobs.store((uint32_t)js.size(), std::memory_order_release);
+            state.store(gen << 32, std::memory_order_release);
+        }
+        cv.notify_all();
+        while (claim_and_copy()) {}
+        while (done.load(std::memory_order_acquire) < js.size()) _mm_pause();
+    }
+};
+std::mutex g_pool_call_mu;                              // one staging copy at a time per process
+CopyPool* g_pool = nullptr;
+}  // namespace
+
+void copy_pool_run(const std::vector<CopyJob>& jobs) {
+    std::lock_guard<std::mutex> lk(g_pool_call_mu);
+    if (g_pool == nullptr || g_pool->owner != getpid()) g_pool = new CopyPool();   // (a forked child leaks the parent's object)
+    g_pool->run(jobs);
+}
+
 }  // namespace vdet
 
 extern "C" {
@@ -116,7 +208,7 @@ int vdet_host_copy_stream_mt(void* dst, const void* src, size_t bytes, int n_thr
     if (n_threads <= 0) {                                   // auto: one core moves ~10 GB/s, the DRAM bus several times that
         const unsigned hw = std::thread::hardware_concurrency() / 2;     // physical cores, roughly
         n_threads = (int)(hw == 0 ? 1 : (hw > 8 ? 8 : hw));
-        if (bytes < (size_t)(4u << 20)) n_threads = 1;      // not worth the thread start-up
+        if (bytes < (size_t)(4u << 20)) n_threads = 1;      // not worth waking the pool
     }
     if (n_threads > 64) n_threads = 64;
     unsigned char* d = static_cast<unsigned char*>(dst);
@@ -129,18 +221,18 @@ int vdet_host_copy_stream_mt(void* dst, const void* src, size_t bytes, int n_thr
     const size_t head = (64 - (reinterpret_cast<uintptr_t>(d) & 63)) & 63;
     const size_t lines = (bytes - head) / 64;
     const size_t per = (lines + n_threads - 1) / n_threads;
-    std::vector<std::thread> pool;
-    pool.reserve(n_threads - 1);
+    std::vector<vdet::CopyJob> jobs;
+    jobs.reserve(n_threads);
+    const size_t first_end = (per < lines) ? head + per * 64 : bytes;
+    jobs.push_back({d, s, first_end});                                      // head + first range
     for (int t = 1; t < n_threads; ++t) {
         const size_t l0 = per * (size_t)t, l1 = (l0 + per < lines) ? l0 + per : lines;
         if (l0 >= l1) break;
         const size_t b0 = head + l0 * 64;
         const size_t b1 = (l1 == lines) ? bytes : head + l1 * 64;          // the last range takes the tail
-        pool.emplace_back(vdet::copy_stream_range, d + b0, s + b0, b1 - b0);
+        jobs.push_back({d + b0, s + b0, b1 - b0});
     }
-    const size_t first_end = (per < lines) ? head + per * 64 : bytes;
-    vdet::copy_stream_range(d, s, first_end);                               // this thread: head + first range
-    for (auto& th : pool) th.join();
+    vdet::copy_pool_run(jobs);
     return VDET_OK;
 }
 

@@ -4,7 +4,9 @@
 // six fields (x1, y1, x2, y2, det_score, anchor) are interpolated linearly over the dense frame
 // range of each tubelet, with linear EXTRApolation one frame beyond either end (extrap1d,
 // tubelet_cls.py:416-428).  Arithmetic follows what the reference executes, in float64:
-//   inside the knots   scipy.interpolate.interp1d(kind='linear') delegates to numpy.interp:
+//   inside the knots   scipy.interpolate.interp1d(kind='linear') delegates to numpy.interp (SciPy >= 0.17; the
+//                      golden vectors were generated with SciPy 1.18.1 / NumPy 2.3.5 -- older SciPy used the
+//                      searchsorted form, which rounds differently AT a knot):
 //                      j = last knot <= x;  x == xs[j] -> ys[j];  else
 //                      slope = (ys[j+1]-ys[j]) / (xs[j+1]-xs[j]);  slope*(x-xs[j]) + ys[j]
 //   left of the knots  ys[0]  + (x-xs[0])  * (ys[1]-ys[0])   / (xs[1]-xs[0])

@@ -880,7 +880,8 @@ __global__ void __launch_bounds__(BIG_THREADS, 1) nms_frames_big_kernel(const Nm
             for (int g = 0; g < Wn; ++g) {
                 const bool valid = (g * 32 + lane) < n;
                 const uint32_t i = valid ? ord[g * 32 + lane] : 0u;
-                const unsigned alive = __ballot_sync(FULL, valid && !removed_bit(rem0, rem1, i));
+                const bool gone = removed_bit(rem0, rem1, i);      // shuffles: every lane takes part, valid or not
+                const unsigned alive = __ballot_sync(FULL, valid && !gone);
                 const bool me_alive = (alive >> lane) & 1u;
                 const uint32_t* myrow = gmask + (size_t)i * W;
                 uint32_t sup_set = 0;                 // bit l2: my box suppresses the candidate in lane l2 (> lane)

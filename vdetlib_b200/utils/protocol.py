@@ -18,9 +18,16 @@ from ..vdet.dataset import imagenet_vdet_classes
 def proto_load(file_path):
     """utils/protocol.py:209-220 (transparent .gz).  A ``.vdetpk`` path -- or a ``.vdetpk`` side-car
     next to the JSON file, preferred like the reference prefers ``.gz`` -- is read from the packed
-    container instead of being parsed as JSON."""
+    container instead of being parsed as JSON.  The side-car is a derived cache: it is used only while it is
+    at least as new as the file it stands for (a regenerated JSON / .gz wins over a stale side-car)."""
     if os.path.splitext(file_path)[1] != '.vdetpk' and os.path.isfile(file_path + '.vdetpk'):
-        file_path += '.vdetpk'
+        sources = [q for q in (file_path, file_path + '.gz') if os.path.isfile(q)]
+        car = file_path + '.vdetpk'
+        if not sources or os.path.getmtime(car) >= max(os.path.getmtime(q) for q in sources):
+            file_path = car
+        else:
+            import logging
+            logging.warning("proto_load: %s is older than %s; ignoring the stale side-car", car, sources[0])
     if os.path.splitext(file_path)[1] == '.vdetpk':
         from .packed import proto_load_packed
         return proto_load_packed(file_path)

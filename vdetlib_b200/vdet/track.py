@@ -70,6 +70,46 @@ def _nms_thres(opts):
     return 0.3
 
 
+def _greedy_loop(vid_proto, state, n_dets, anchor_of, score_of, track_method, opts, nms_thres):
+    """The outer loop both greedy trackers share (vdet/track.py:141-185 and :206-251): take the best detection that
+    is still alive, stop below ``opts.thres`` or at ``opts.max_tracks``, track it with the external tracker, then
+    drop every detection the new tracklets suppress.  ``anchor_of(i) -> (frame, bbox)``, ``score_of(i)``.
+
+    The reference retries a failed ``track_method`` call once after restarting its MATLAB engine (:159-168).  The
+    engine is out of scope here; the control flow is kept through ``opts.on_tracker_error`` (optional callable,
+    e.g. one that restarts the caller's tracker backend): when the tracker raises, the hook runs and the call is
+    retried once; without a hook the exception propagates."""
+    keep = [True] * n_dets
+    cur_top_det_id = 0
+    tracks = []
+    while np.any(keep) and len(tracks) < opts.max_tracks:
+        while cur_top_det_id < len(keep) and not keep[cur_top_det_id]:
+            cur_top_det_id += 1
+        if cur_top_det_id == len(keep):
+            break
+        top = cur_top_det_id
+        cur_top_det_id += 1
+        if score_of(top) < opts.thres:
+            logging.info("Upon low confidence: total {} tracks".format(len(tracks)))
+            break
+        logging.info("tracking top No.{} in {}".format(len(tracks), vid_proto['video']))
+        anchor_frame_id, anchor_bbox = anchor_of(top)
+        try:
+            new_tracks = track_method(vid_proto, anchor_frame_id, anchor_bbox, opts)
+        except Exception:
+            hook = getattr(opts, 'on_tracker_error', None)
+            if hook is None:
+                raise
+            hook(opts)
+            new_tracks = track_method(vid_proto, anchor_frame_id, anchor_bbox, opts)
+        tracks.extend(new_tracks)
+        logging.info("Applying nms between new tracks ({}) and detections.".format(len(new_tracks)))
+        state.suppress(new_tracks, nms_thres)
+        keep = state.keep_host()
+        logging.info("{} / {} boxes kept.".format(np.sum(keep), len(keep)))
+    return tracks
+
+
 def greedily_track_from_det(vid_proto, det_proto, track_method, score_fun, opts):
     '''greedily track top detections and supress detections
        that have large overlaps with tracked boxes  (vdet/track.py:122-186)'''
@@ -82,30 +122,10 @@ def greedily_track_from_det(vid_proto, det_proto, track_method, score_fun, opts)
     dets = sorted(det_proto['detections'], key=lambda x: score_fun(x), reverse=True)
     det_info = np.asarray([[det['frame'], ] + list(det['bbox']) + [score_fun(det), ]
                            for det in dets], dtype=np.float32).reshape(-1, 6)
-    state = _GreedyState(det_info)
-    keep = [True] * len(dets)
-    cur_top_det_id = 0
-    tracks = []
-    while np.any(keep) and len(tracks) < opts.max_tracks:
-        while cur_top_det_id < len(keep) and not keep[cur_top_det_id]:
-            cur_top_det_id += 1
-        if cur_top_det_id == len(keep):
-            break
-        top_det = dets[cur_top_det_id]
-        cur_top_det_id += 1
-        if score_fun(top_det) < opts.thres:
-            logging.info("Upon low confidence: total {} tracks".format(len(tracks)))
-            break
-        logging.info("tracking top No.{} in {}".format(len(tracks), vid_proto['video']))
-        anchor_frame_id = top_det['frame']
-        anchor_bbox = list(map(int, top_det['bbox']))
-        new_tracks = track_method(vid_proto, anchor_frame_id, anchor_bbox, opts)
-        tracks.extend(new_tracks)
-        logging.info("Applying nms between new tracks ({}) and detections.".format(len(new_tracks)))
-        state.suppress(new_tracks, nms_thres)
-        keep = state.keep_host()
-        logging.info("{} / {} boxes kept.".format(np.sum(keep), len(keep)))
-    track_proto['tracks'] = tracks
+    track_proto['tracks'] = _greedy_loop(
+        vid_proto, _GreedyState(det_info), len(dets),
+        lambda i: (dets[i]['frame'], list(map(int, dets[i]['bbox']))), lambda i: score_fun(dets[i]),
+        track_method, opts, nms_thres)
     return track_proto
 
 
@@ -119,28 +139,8 @@ def greedily_track_from_raw_dets(vid_proto, det_info, track_method, class_idx, o
 
     det_info = np.asarray(sorted(det_info[:, [0, 1, 2, 3, 4, 4 + class_idx]],
                                  key=itemgetter(5), reverse=True), dtype=np.float32).reshape(-1, 6)
-    state = _GreedyState(det_info)
-    keep = [True] * len(det_info)
-    cur_top_det_id = 0
-    tracks = []
-    while np.any(keep) and len(tracks) < opts.max_tracks:
-        while cur_top_det_id < len(keep) and not keep[cur_top_det_id]:
-            cur_top_det_id += 1
-        if cur_top_det_id == len(keep):
-            break
-        top_det = det_info[cur_top_det_id]
-        cur_top_det_id += 1
-        if top_det[-1] < opts.thres:
-            logging.info("Upon low confidence: total {} tracks".format(len(tracks)))
-            break
-        logging.info("tracking top No.{} in {}".format(len(tracks), vid_proto['video']))
-        anchor_frame_id = int(top_det[0])
-        anchor_bbox = list(map(int, top_det[1:5]))
-        new_tracks = track_method(vid_proto, anchor_frame_id, anchor_bbox, opts)
-        tracks.extend(new_tracks)
-        logging.info("Applying nms between new tracks ({}) and detections.".format(len(new_tracks)))
-        state.suppress(new_tracks, nms_thres)
-        keep = state.keep_host()
-        logging.info("{} / {} boxes kept.".format(np.sum(keep), len(keep)))
-    track_proto['tracks'] = tracks
+    track_proto['tracks'] = _greedy_loop(
+        vid_proto, _GreedyState(det_info), len(det_info),
+        lambda i: (int(det_info[i][0]), list(map(int, det_info[i][1:5]))), lambda i: det_info[i][-1],
+        track_method, opts, nms_thres)
     return track_proto

@@ -472,6 +472,10 @@ def score_proto_interpolation(score_proto, vid_proto):
         for t_i in todo:
             boxes = score_proto['tubelets'][t_i]['boxes']
             idx = np.asarray([b['frame'] for b in boxes])
+            if len(set(idx.tolist())) != len(idx):
+                # two boxes on one frame: interp1d divides by a zero knot spacing (nan / inf with a warning); the
+                # result is undefined in the reference, refused here
+                raise ValueError('score_proto_interpolation: tubelet {} has two boxes on the same frame'.format(t_i))
             order = np.argsort(idx, kind='mergesort')          # interp1d sorts its x (assume_sorted=False)
             vals = [[b['bbox'][0] for b in boxes], [b['bbox'][1] for b in boxes], [b['bbox'][2] for b in boxes],
                     [b['bbox'][3] for b in boxes], [b['det_score'] for b in boxes], [b['anchor'] for b in boxes]]
