@@ -376,6 +376,41 @@ def test_video_postprocessor_streams_new_shards_from_pageable_memory(graph):
         check(pp.collect(pp.submit_host(*shards[k], graph=graph)), *shards[k])
 
 
+def test_video_postprocessor_registered_caller_arrays():
+    """register_host_arrays: caller-owned arrays pinned in place are uploaded from directly (no staging copy), eager
+    and graph replay (one graph per source array), mixed with ordinary pageable shards; unregistering falls back."""
+    from vdetlib_b200.vdet.video_det import VideoPostProcessor
+    T, N, C = 8, 160, 4
+    pp = VideoPostProcessor(T, N, C, 0.3, n_chunks=2)
+    shards = [synth.boxes_scores(T, N, C, seed=970 + k) for k in range(3)]
+    want = [c_oracle.nms_frames(b, s, 0.3) for b, s in shards]
+    links = [c_oracle.link_f32(b) for b, _ in shards]
+    pp.register_host_arrays(*[a for sh in shards[:2] for a in sh])          # the third shard stays pageable
+
+    def check(out, k):
+        km, ki, kc = want[k]
+        assert np.array_equal(out["keep_cnt"], kc) and np.array_equal(out.keep_mask(), km)
+        got = out["succ"][:(T - 1) * N].reshape(T - 1, N) - np.arange(1, T)[:, None] * N
+        assert np.array_equal(got, links[k][0])
+
+    for graph in (False, True):
+        order = [0, 1, 2, 1, 0, 2, 0]
+        t = pp.submit_host(*shards[order[0]], graph=graph)
+        for prev, k in zip(order, order[1:]):
+            t2 = pp.submit_host(*shards[k], graph=graph)
+            check(pp.collect(t), prev)
+            t = t2
+        check(pp.collect(t), order[-1])
+    assert pp._src[0][0].data_ptr() != pp.h_boxes_sets[0].data_ptr() or pp._src[1][0].data_ptr() != pp.h_boxes_sets[1].data_ptr()
+    pp.unregister_host_arrays()
+    assert not pp._registered
+    for k in (0, 1):
+        check(pp.collect(pp.submit_host(*shards[k], graph=True)), k)
+        assert pp._src[0][0].data_ptr() == pp.h_boxes_sets[0].data_ptr()
+    with pytest.raises(ValueError):
+        pp.register_host_arrays(shards[0][0].astype(np.float64))
+
+
 def test_video_postprocessor_ragged_frames():
     """Ragged shards (packed rows + counts) through the staged pipeline, chunk edges balanced by rows."""
     from vdetlib_b200.vdet.video_det import VideoPostProcessor

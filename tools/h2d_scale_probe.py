@@ -152,7 +152,29 @@ def main():
         th.join()
         return up * n, down * n
 
-    legs = [("h2d", leg_h2d), ("d2h", leg_d2h), ("duplex", leg_duplex), ("stage", leg_stage),
+    cudart = torch.cuda.cudart()
+
+    def leg_register(n):
+        # pin the producer's pageable shard in place (cudaHostRegister), upload from it, unpin: no staging copy at all
+        for k in range(n):
+            a = src[k % 3]
+            rc = cudart.cudaHostRegister(a.ctypes.data, up, 0)
+            assert int(rc) == 0, rc
+            t = torch.from_numpy(a)
+            with torch.cuda.stream(s1):
+                d_up.copy_(t, non_blocking=True)
+            s1.synchronize()
+            cudart.cudaHostUnregister(a.ctypes.data)
+        return up * n, 0
+
+    def leg_register_only(n):
+        for k in range(n):
+            a = src[k % 3]
+            cudart.cudaHostRegister(a.ctypes.data, up, 0)
+            cudart.cudaHostUnregister(a.ctypes.data)
+        return up * n, 0
+
+    legs = [("register_only", leg_register_only), ("register+h2d", leg_register), ("h2d", leg_h2d), ("d2h", leg_d2h), ("duplex", leg_duplex), ("stage", leg_stage),
             ("stage+h2d", leg_stage_h2d), ("stage_thread+h2d", leg_stage_thread_h2d)]
     out = {}
     for name, fn in legs:

@@ -20,13 +20,13 @@
 #include "common.cuh"
 #include "warp_sort.cuh"
 
-// Experiments (off in the product build; tools/build_variant.py builds them as separate libraries):
-//   VDET_EXP_PURE_LDS  the rank search reads the sorted keys through NON-volatile asm loads, which the compiler may
+// Build switches (tools/build_variant.py builds the other setting as a separate library for A/B timing):
+//   VDET_EXP_PURE_LDS  (1 = default since round 2: 0.3497 ms against 0.3528 on config 2) the rank search reads the sorted keys through NON-volatile asm loads, which the compiler may
 //                      interleave across the elements of a lane (the volatile form keeps them in program order: one
 //                      probe chain at a time).  Ordering after the key stores comes from a data dependence: every
 //                      probe address contains a token that is defined after the __syncwarp().
 #ifndef VDET_EXP_PURE_LDS
-#define VDET_EXP_PURE_LDS 0
+#define VDET_EXP_PURE_LDS 1
 #endif
 //   VDET_TILE_PACKED   the 32x32 bit-matrix tile evaluates two columns per step on packed float32 pairs
 //                      (FADD2 / FMUL2); 0 = the scalar tile of round 1, kept for A/B timing.
@@ -870,67 +870,51 @@ __global__ void __launch_bounds__(BIG_THREADS, 1) nms_frames_big_kernel(const Nm
             uint8_t* out_m = p.keep_mask ? p.keep_mask + blk : nullptr;
             const unsigned lt = lanemask_lt();
             const bool my_words = 2 * lane < W;
-            // Greedy walk, 32 candidates of the score order per step, three phases per step so that no
-            // global load depends on another one of the same step:
-            //   1. every still-alive candidate gathers, from its own mask row, the bits of the later
-            //      alive candidates of the step (independent loads, 8 in flight per lane);
-            //   2. the step's greedy choice is resolved on those 32x32 bits in registers;
-            //   3. the rows of the kept boxes are ORed into the removed set (independent loads, 4 in flight).
+            // Greedy walk, 32 candidates of the score order per step.  The mask rows of the step's still-alive
+            // candidates are fetched up to 8 at a time (independent 8-byte loads per lane, one L2 latency per
+            // batch), then the batch is resolved in order in registers: a candidate that is still alive at its
+            // turn is kept, its row is ORed into the removed set and -- through two shuffles and a ballot -- kills
+            // the later candidates of the step it suppresses; a candidate killed earlier in the batch is skipped
+            // (its row was fetched for nothing: bandwidth, not latency).  One row load per candidate serves both
+            // the in-step resolution and the removed set.
 #pragma unroll 1
             for (int g = 0; g < Wn; ++g) {
                 const bool valid = (g * 32 + lane) < n;
                 const uint32_t i = valid ? ord[g * 32 + lane] : 0u;
                 const bool gone = removed_bit(rem0, rem1, i);      // shuffles: every lane takes part, valid or not
-                const unsigned alive = __ballot_sync(FULL, valid && !gone);
-                const bool me_alive = (alive >> lane) & 1u;
-                const uint32_t* myrow = gmask + (size_t)i * W;
-                uint32_t sup_set = 0;                 // bit l2: my box suppresses the candidate in lane l2 (> lane)
-                for (unsigned m = alive & (alive - 1); m;) {      // the first alive candidate is nobody's "later"
-                    int l2[8];
-                    uint32_t i2[8], w[8];
+                unsigned alive = __ballot_sync(FULL, valid && !gone);
+                const int wi = (int)(i >> 5);
+                const int src_lane = (wi >> 1) & 31;               // lane holding my candidate's word of a fetched row
+                const bool odd = (wi & 1) != 0;
+                const uint32_t ibit = 1u << (i & 31);
+                unsigned kgrp = 0;
+                while (alive) {
+                    uint2 r[8];
+                    int ls[8];
+                    unsigned t = alive;
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        l2[q] = m ? (__ffs(m) - 1) : 32;
-                        m &= m - 1;
-                        i2[q] = __shfl_sync(FULL, i, l2[q] & 31);
+                        ls[q] = t ? (__ffs(t) - 1) : -1;
+                        t &= t - 1;
+                        const uint32_t ci = __shfl_sync(FULL, i, ls[q] & 31);
+                        r[q] = (ls[q] >= 0 && my_words)
+                                   ? __ldcg(reinterpret_cast<const uint2*>(gmask + (size_t)ci * W) + lane)
+                                   : make_uint2(0u, 0u);
                     }
 #pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        w[q] = (me_alive && l2[q] > lane && l2[q] < 32) ? __ldcg(myrow + (i2[q] >> 5)) : 0u;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) sup_set |= ((w[q] >> (i2[q] & 31)) & 1u) << (l2[q] & 31);
-                }
-                unsigned kgrp = 0;
-                for (unsigned a = alive; a;) {
-                    const int l = __ffs(a) - 1;
-                    kgrp |= (1u << l);
-                    a &= ~(1u << l);
-                    a &= ~__shfl_sync(FULL, sup_set, l);
-                }
-                if (!check_zero) {
-                    for (unsigned m = kgrp; m;) {
-                        uint2 r[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int l = m ? (__ffs(m) - 1) : -1;
-                            m &= m - 1;
-                            const uint32_t ci = __shfl_sync(FULL, i, l & 31);
-                            r[q] = (l >= 0 && my_words)
-                                       ? __ldcg(reinterpret_cast<const uint2*>(gmask + (size_t)ci * W) + lane)
-                                       : make_uint2(0u, 0u);
-                        }
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) { rem0 |= r[q].x; rem1 |= r[q].y; }
-                    }
-                } else {
-                    for (unsigned m = kgrp; m; m &= m - 1) {
-                        const int l = __ffs(m) - 1;
-                        const uint32_t ci = __shfl_sync(FULL, i, l);
-                        zero_division_check_big(p.boxes, p.box_ld, p.box_vec, p.status, srow, ord, n, rem0, rem1, ci, g * 32 + l, lane);
-                        if (my_words) {
-                            const uint2 r = __ldcg(reinterpret_cast<const uint2*>(gmask + (size_t)ci * W) + lane);
-                            rem0 |= r.x;
-                            rem1 |= r.y;
+                    for (int q = 0; q < 8; ++q) {
+                        if (ls[q] >= 0 && ((alive >> ls[q]) & 1u)) {             // warp-uniform
+                            if (check_zero) {
+                                const uint32_t ci = __shfl_sync(FULL, i, ls[q]);
+                                zero_division_check_big(p.boxes, p.box_ld, p.box_vec, p.status, srow, ord, n, rem0, rem1, ci,
+                                                        g * 32 + ls[q], lane);
+                            }
+                            kgrp |= 1u << ls[q];
+                            rem0 |= r[q].x;
+                            rem1 |= r[q].y;
+                            const uint32_t w0 = __shfl_sync(FULL, r[q].x, src_lane), w1 = __shfl_sync(FULL, r[q].y, src_lane);
+                            const unsigned dead = __ballot_sync(FULL, ((odd ? w1 : w0) & ibit) != 0u);
+                            alive &= ~(dead | (1u << ls[q]));
                         }
                     }
                 }

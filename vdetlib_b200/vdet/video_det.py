@@ -7,6 +7,7 @@ BASELINE.json benchmarks); it avoids the proto-dict walk that dominates the refe
 """
 import copy
 import logging
+import time
 
 import numpy as np
 import torch
@@ -118,7 +119,7 @@ class _Slot(object):
         self.done = torch.cuda.Event()
         self.busy = False
         self.shape = None                                   # (n_frames, rows) of the step in flight
-        self.graph = None                                   # whole-step CUDA graph (uniform frames)
+        self.graphs = {}                                    # whole-step CUDA graphs (uniform frames), per upload source
         self.launch_stream = torch.cuda.Stream(device=dev)  # the graph of this slot is launched here
         # frames of more than 1024 boxes keep their bit matrix in a global scratch slot per CTA
         self.ws_bytes = _lib.load().vdet_nms_frames_workspace_bytes(N, C, dev.index or 0) if N > 1024 else 0
@@ -175,6 +176,8 @@ class VideoPostProcessor(object):
         self.h_scores_sets = [torch.empty((rows, C), dtype=torch.float32).pin_memory() for _ in range(n_stage)]
         self.h_seg_sets = [torch.from_numpy(self._uniform_off.copy()).pin_memory() for _ in range(n_stage)]
         self._staged = [None] * n_stage                     # per staging set: (n_frames, rows, uniform) of its shard
+        self._src = [(self.h_boxes_sets[k], self.h_scores_sets[k]) for k in range(n_stage)]   # what the step uploads from
+        self._registered = {}                               # data pointer -> (array kept alive, pinned tensor view)
         self.h_boxes, self.h_scores = self.h_boxes_sets[0], self.h_scores_sets[0]
         # frame ranges of the pipeline chunks (uniform shards; ragged ones balance rows per step)
         self.n_chunks = max(1, min(int(n_chunks), T))
@@ -185,6 +188,10 @@ class VideoPostProcessor(object):
         self._next_slot = 0
         self._graphs = {}
         self._lib = _lib.load()
+        # host-side wall clock of the staged path, accumulated per step (what bounds the end-to-end rate on a
+        # host-bound box): [stage copy, enqueue / graph launch, wait in collect], in seconds
+        self.host_s = [0.0, 0.0, 0.0]
+        self.host_steps = 0
 
     def _chunk_edges(self, off, n_frames):
         """Frame ranges whose row counts are as equal as the frame boundaries allow."""
@@ -262,6 +269,34 @@ class VideoPostProcessor(object):
             self._next_slot = 0
         return self.slots[self._next_slot]
 
+    def register_host_arrays(self, *arrays):
+        """Pin caller-owned C-contiguous float32 NumPy arrays IN PLACE (cudaHostRegister) so that later
+        ``stage`` / ``submit_host`` calls given exactly these arrays upload straight from them -- no staging copy,
+        i.e. a third of the host-memory traffic of the general path (the producer's write + one DMA read instead
+        of + a read and a write of the copy).  For producers that fill a fixed ring of output buffers.  The
+        arrays are kept alive by the processor and must not be modified between ``submit_host`` and
+        ``collect`` of a step that uses them.  ``unregister_host_arrays`` undoes it."""
+        cudart = torch.cuda.cudart()
+        for a in arrays:
+            if not (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]):
+                raise ValueError("register_host_arrays: C-contiguous float32 NumPy arrays only")
+            if a.ctypes.data in self._registered:
+                continue
+            rc = cudart.cudaHostRegister(a.ctypes.data, a.nbytes, 0)
+            if int(rc) != 0:
+                raise RuntimeError("cudaHostRegister failed: %r" % (rc,))
+            self._registered[a.ctypes.data] = (a, torch.from_numpy(a))
+
+    def unregister_host_arrays(self, *arrays):
+        if any(sl.busy for sl in self.slots):
+            raise RuntimeError("unregister_host_arrays: collect() the steps in flight first")
+        for sl in self.slots:
+            sl.graphs.clear()                               # captured uploads may point at these arrays
+        cudart = torch.cuda.cudart()
+        for a in (arrays or [v[0] for v in list(self._registered.values())]):
+            if self._registered.pop(a.ctypes.data, None) is not None:
+                cudart.cudaHostUnregister(a.ctypes.data)
+
     def stage(self, boxes, scores, counts=None):
         """Copy host arrays (pageable or not) into the pinned upload buffers of the NEXT step to be submitted,
         with streaming stores over several host threads: lines written with ordinary stores stay dirty in the
@@ -290,9 +325,15 @@ class VideoPostProcessor(object):
             seg[0] = 0
             np.cumsum(cnt, out=seg[1:n_frames + 1])
             seg[n_frames + 1:] = rows
-        if rows:
-            ops.host_copy_stream(target.h_boxes[:rows], b, self.stage_threads)
-            ops.host_copy_stream(target.h_scores[:rows], s, self.stage_threads)
+        rb, rs = self._registered.get(b.ctypes.data), self._registered.get(s.ctypes.data)
+        if rb is not None and rs is not None and rb[0].nbytes >= b.nbytes and rs[0].nbytes >= s.nbytes:
+            # the caller's own arrays, pinned in place: the step uploads from them directly
+            self._src[target.stage_set] = (rb[1].view(-1, 4), rs[1].view(-1, self.C))
+        else:
+            if rows:
+                ops.host_copy_stream(target.h_boxes[:rows], b, self.stage_threads)
+                ops.host_copy_stream(target.h_scores[:rows], s, self.stage_threads)
+            self._src[target.stage_set] = (target.h_boxes, target.h_scores)
         self._staged[target.stage_set] = (n_frames, rows, uniform)
 
     # ---- one step on the streams -----------------------------------------------------------
@@ -308,6 +349,7 @@ class VideoPostProcessor(object):
         s_in, s_out = self.s_in, self.s_out
         off = self._uniform_off if uniform else sl.h_seg.numpy()
         chunks = self.chunks if uniform else self._chunk_edges(off, n_frames)
+        h_boxes, h_scores = self._src[sl.stage_set]
         if fork:
             s_in.wait_stream(cur)
             s_out.wait_stream(cur)
@@ -315,12 +357,12 @@ class VideoPostProcessor(object):
         with torch.cuda.stream(s_in):
             sl.d_seg.copy_(sl.h_seg, non_blocking=True)       # 4 KB: the step's segment table (uniform or ragged)
             if rows:
-                sl.d_boxes[:rows].copy_(sl.h_boxes[:rows], non_blocking=True)
+                sl.d_boxes[:rows].copy_(h_boxes[:rows], non_blocking=True)
             sl.ev_boxes.record(s_in)
             for k, (f0, f1) in enumerate(chunks):
                 r0, r1 = int(off[f0]), int(off[f1])
                 if r1 > r0:
-                    sl.d_scores[r0:r1].copy_(sl.h_scores[r0:r1], non_blocking=True)
+                    sl.d_scores[r0:r1].copy_(h_scores[r0:r1], non_blocking=True)
                 sl.ev_in[k].record(s_in)
         cur.wait_event(sl.ev_boxes)
         seg = sl.d_seg[:n_frames + 1]
@@ -363,8 +405,7 @@ class VideoPostProcessor(object):
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=sl.launch_stream):
             self._enqueue(sl, shape, halo, halo_count, fork=True)
-        sl.graph = g
-        sl.graph_key = (0 if halo is None else halo.data_ptr(), 0 if halo_count is None else halo_count.data_ptr())
+        return g
 
     def submit_staged(self, halo=None, halo_fn=None, graph=False, halo_count=None):
         """Enqueue one step on the next free slot from its staged inputs and return a ticket for
@@ -383,19 +424,25 @@ class VideoPostProcessor(object):
         if shape is None:
             raise RuntimeError("submit_staged: nothing staged; call stage() first")
         n_frames, rows, uniform = shape
+        src_boxes, src_scores = self._src[sl.stage_set]
         if graph and uniform:
             with torch.cuda.stream(sl.launch_stream):
                 if halo_fn is not None:
-                    halo, halo_count = halo_fn(k, sl.h_boxes[:int(self._uniform_off[1])])
-                key = (0 if halo is None else halo.data_ptr(), 0 if halo_count is None else halo_count.data_ptr())
-                if sl.graph is None or sl.graph_key != key:
-                    self._capture(sl, shape, halo, halo_count)
-                sl.graph.replay()
+                    halo, halo_count = halo_fn(k, src_boxes[:int(self._uniform_off[1])])
+                # one graph per (upload source, halo buffers): the pinned staging set, or a registered caller array
+                key = (src_boxes.data_ptr(), src_scores.data_ptr(), 0 if halo is None else halo.data_ptr(),
+                       0 if halo_count is None else halo_count.data_ptr())
+                g = sl.graphs.get(key)
+                if g is None:
+                    if len(sl.graphs) >= 16:
+                        sl.graphs.clear()
+                    g = sl.graphs[key] = self._capture(sl, shape, halo, halo_count)
+                g.replay()
                 sl.done.record(sl.launch_stream)
         else:
             if halo_fn is not None:
                 first = int(sl.h_seg[1].item()) if not uniform else self.N
-                halo, halo_count = halo_fn(k, sl.h_boxes[:first])
+                halo, halo_count = halo_fn(k, src_boxes[:first])
             self._enqueue(sl, shape, halo, halo_count, fork=False)
         sl.shape = shape
         sl.busy = True
@@ -405,8 +452,14 @@ class VideoPostProcessor(object):
     def submit_host(self, boxes, scores, counts=None, halo=None, halo_fn=None, graph=True, halo_count=None):
         """The user-facing asynchronous call: stage the host arrays (this is where the caller's memory is read;
         the arrays may be reused as soon as this returns) and enqueue the step.  Returns a ticket."""
+        t0 = time.perf_counter()
         self.stage(boxes, scores, counts)
-        return self.submit_staged(halo, halo_fn, graph, halo_count)
+        t1 = time.perf_counter()
+        ticket = self.submit_staged(halo, halo_fn, graph, halo_count)
+        self.host_s[0] += t1 - t0
+        self.host_s[1] += time.perf_counter() - t1
+        self.host_steps += 1
+        return ticket
 
     def collect(self, ticket):
         """Wait for the step behind ``ticket``; returns a :class:`StepResult` of host views (valid until the
@@ -414,7 +467,9 @@ class VideoPostProcessor(object):
         sl = self.slots[ticket]
         if not sl.busy:
             raise RuntimeError("collect: ticket %r is not in flight" % (ticket,))
+        t0 = time.perf_counter()
         sl.done.synchronize()
+        self.host_s[2] += time.perf_counter() - t0
         sl.busy = False
         ops.raise_for_status_word(int(sl.h_status.item()))
         n_frames, rows, uniform = sl.shape
