@@ -404,6 +404,8 @@ def test_video_postprocessor_registered_caller_arrays():
     assert pp._src[0][0].data_ptr() != pp.h_boxes_sets[0].data_ptr() or pp._src[1][0].data_ptr() != pp.h_boxes_sets[1].data_ptr()
     pp.unregister_host_arrays()
     assert not pp._registered
+    with pytest.raises(RuntimeError):
+        pp.submit_staged(graph=True)             # the staged shard was a caller array that is no longer pinned
     for k in (0, 1):
         check(pp.collect(pp.submit_host(*shards[k], graph=True)), k)
         assert pp._src[0][0].data_ptr() == pp.h_boxes_sets[0].data_ptr()

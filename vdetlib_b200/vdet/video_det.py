@@ -296,6 +296,13 @@ class VideoPostProcessor(object):
         for a in (arrays or [v[0] for v in list(self._registered.values())]):
             if self._registered.pop(a.ctypes.data, None) is not None:
                 cudart.cudaHostUnregister(a.ctypes.data)
+        # a staging set that still names an array which is no longer pinned has nothing staged any more
+        live = set(v[1].data_ptr() for v in self._registered.values())
+        for k, (sb, ss) in enumerate(self._src):
+            own = (self.h_boxes_sets[k].data_ptr(), self.h_scores_sets[k].data_ptr())
+            if (sb.data_ptr(), ss.data_ptr()) != own and not (sb.data_ptr() in live and ss.data_ptr() in live):
+                self._src[k] = (self.h_boxes_sets[k], self.h_scores_sets[k])
+                self._staged[k] = None
 
     def stage(self, boxes, scores, counts=None):
         """Copy host arrays (pageable or not) into the pinned upload buffers of the NEXT step to be submitted,
