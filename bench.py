@@ -555,6 +555,8 @@ def run_b200(args):
     e1.record()
     barrier()
     wall_ms = (time.perf_counter() - w0) * 1e3 / K
+    host_ms = {"stage_copy": 1e3 * pp.pp.host_s[0] / K, "enqueue": 1e3 * pp.pp.host_s[1] / K,
+               "wait_in_collect": 1e3 * pp.pp.host_s[2] / K}
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / K
     last = (K - 1) % NSETS
     res = {k: np.array(res[k], copy=True) for k in ("keep_off", "keep_idx", "keep_cnt", "succ", "link_iou")}
@@ -573,8 +575,7 @@ def run_b200(args):
     pinned_ms = e2e_time(max(K, 20), fresh=False)
     e2e = {"value": world * T * N / (e2e_ms / 1000.0), "unit": "boxes/s", "ms_per_step": e2e_ms,
            "host_wall_ms_per_step": wall_ms,
-           "host_ms_per_step": {"stage_copy": 1e3 * pp.pp.host_s[0] / K, "enqueue": 1e3 * pp.pp.host_s[1] / K,
-                                "wait_in_collect": 1e3 * pp.pp.host_s[2] / K},
+           "host_ms_per_step": host_ms,
            "h2d_bytes_per_step": pp.pp.h2d_bytes, "d2h_bytes_per_step": d2h,
            "input": "a different shard every step from pageable NumPy arrays (%d rotating shards); the copy into the "
                     "pinned upload buffers (%d host threads) is inside the timed region" % (NSETS, pp.pp.stage_threads or 8),

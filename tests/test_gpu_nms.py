@@ -119,6 +119,7 @@ def test_strided_and_wide_input():
 
 
 @pytest.mark.parametrize("T,N,C,thr", [(17, 300, 30, 0.3), (5, 64, 1, 0.5), (9, 33, 7, 0.3), (3, 1000, 4, 0.3),
+                                      (4, 150, 9, 0.3), (4, 190, 9, 0.3), (4, 257, 9, 0.3), (4, 320, 9, 0.5), (4, 380, 9, 0.3),
                                         (3, 1025, 2, 0.3), (160, 2000, 3, 0.3), (2, 2048, 2, 0.5)])
 def test_nms_frames_vs_oracle(T, N, C, thr):
     b, s = synth.boxes_scores(T, N, C, seed=T * 1000 + N)
@@ -404,8 +405,9 @@ def test_video_postprocessor_registered_caller_arrays():
     assert pp._src[0][0].data_ptr() != pp.h_boxes_sets[0].data_ptr() or pp._src[1][0].data_ptr() != pp.h_boxes_sets[1].data_ptr()
     pp.unregister_host_arrays()
     assert not pp._registered
+    assert pp._staged[0] is None and pp._staged[1] is not None       # slot 0 had a caller array, slot 1 the pageable shard
     with pytest.raises(RuntimeError):
-        pp.submit_staged(graph=True)             # the staged shard was a caller array that is no longer pinned
+        pp.run_staged(graph=True)                # slot 0: its staged shard was a caller array that is no longer pinned
     for k in (0, 1):
         check(pp.collect(pp.submit_host(*shards[k], graph=True)), k)
         assert pp._src[0][0].data_ptr() == pp.h_boxes_sets[0].data_ptr()
