@@ -20,7 +20,7 @@ el "h2d probe"
 for n in 1 2 4 8; do
   [ $n -le $NG ] || continue
   timeout 120 bash -c "$(declare -f run_n); PORT=$((29700 + n)); run_n $n tools/h2d_scale_probe.py --reps 30" >> gpurun_out/h2d_probe_scale.json 2>> gpurun_out/multi.err
-  if [ $n -gt 1 ]; then
+  if [ $n -ge 4 ]; then
     timeout 120 bash -c "$(declare -f run_n); PORT=$((29750 + n)); run_n $n tools/h2d_scale_probe.py --reps 30 --bind" >> gpurun_out/h2d_probe_scale.json 2>> gpurun_out/multi.err
   fi
 done

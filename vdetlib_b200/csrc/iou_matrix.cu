@@ -132,10 +132,10 @@ __device__ __forceinline__ double pair_iou_f64(const double ax1, const double ay
                                                const double ay2, const double aa, const double bx1,
                                                const double by1, const double bx2, const double by2,
                                                const double ba) {
-    const double ix1 = fmax(ax1, bx1), ix2 = fmin(ax2, bx2);
-    const double iy1 = fmax(ay1, by1), iy2 = fmin(ay2, by2);
-    const double iw = fmax(0.0, __dadd_rn(__dsub_rn(ix2, ix1), 1.0));
-    const double ih = fmax(0.0, __dadd_rn(__dsub_rn(iy2, iy1), 1.0));
+    const double ix1 = dmax_np(ax1, bx1), ix2 = dmin_np(ax2, bx2);
+    const double iy1 = dmax_np(ay1, by1), iy2 = dmin_np(ay2, by2);
+    const double iw = dmax_np(0.0, __dadd_rn(__dsub_rn(ix2, ix1), 1.0));
+    const double ih = dmax_np(0.0, __dadd_rn(__dsub_rn(iy2, iy1), 1.0));
     const double inter = __dmul_rn(iw, ih);
     return __ddiv_rn(inter, __dsub_rn(__dadd_rn(aa, ba), inter));
 }

@@ -108,13 +108,12 @@ extern "C" int vdet_nms_frames_f32(const float* boxes, int box_ld,
     p.nb = nb;
     int nper = 1;                                                           // sort network: 32*nper >= nb
     while (32 * nper < nb) nper <<= 1;
-    // a frame that fills at most 5/8 or 3/4 of the power-of-two network sorts two arrays instead (A = half the
-    // network, B = a quarter / an eighth of it: 300 boxes -> 256 + 64 keys), see nms_frames.cuh
+    // a frame that fills at most 5/8 of the power-of-two network sorts two arrays instead (A = half the network,
+    // B = an eighth of it: 300 boxes -> 256 + 64 keys), see nms_frames.cuh
     int npb = 0;
-    if (nper == 8 || nper == 16) {
-        if (nb <= 32 * (nper / 2 + nper / 8)) { npb = nper / 8; nper /= 2; }
-        else if (nb <= 32 * (nper / 2 + nper / 4)) { npb = nper / 4; nper /= 2; }
-    }
+    // (measured on B200, 1000 frames x 30 classes: 300 boxes 0.326 ms against 0.351, 150 boxes 0.146 against 0.152;
+    // a 3/4 split -- 190 boxes as 128 + 64, 380 as 256 + 128 -- is slower than the padded network and is not built)
+    if ((nper == 8 || nper == 16) && nb <= 32 * (nper / 2 + nper / 8)) { npb = nper / 8; nper /= 2; }
     if (const char* e = getenv("VDET_NMS_NO_SPLIT")) {                      // measurement hook: the single-array network
         if (atoi(e) && npb) { nper *= 2; npb = 0; }
     }

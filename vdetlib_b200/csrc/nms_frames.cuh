@@ -237,7 +237,7 @@ static __device__ __noinline__ void zero_division_check(const uint32_t* so, int 
 // STAGE: the frame's scores are transposed into shared memory (as sort keys) in phase A; a
 // compile-time switch, so the per-element key fetch carries no trace of the other path.
 // NPB > 0: the class's keys are sorted as TWO arrays, A = the first 32*NPER elements and B = the next 32*NPB
-// (NPB = NPER/4 or NPER/2), and an element's rank is the sum of its lower bounds in both.  A 300-box frame then
+// (NPB = NPER/4), and an element's rank is the sum of its lower bounds in both.  A 300-box frame then
 // sorts 256 + 64 keys (330 compare-exchanges per lane) instead of padding to a 512-key network (720): the
 // network was the largest single item of the per-class work, the two extra probe chains cost a
 // third of what it saves.

@@ -1,5 +1,5 @@
 // nms_frames_split.cu -- the two-array sort variants of nms_frames_kernel (nms_frames.cuh): frames that fill at
-// most 5/8 or 3/4 of a power-of-two sort network (129..192 and 257..384 boxes; BASELINE's 300-box frames sort
+// most 5/8 of a power-of-two sort network (129..160 and 257..320 boxes; BASELINE's 300-box frames sort
 // 256 + 64 keys).  A translation unit of its own so that the instantiations compile beside the others.
 #include "nms_frames.cuh"
 
@@ -13,9 +13,7 @@ static int launch_split(const NmsFramesParams& p, size_t smem, int grid, cudaStr
 
 int launch_nms_frames_split(int nper, int npb, const NmsFramesParams& p, size_t smem, int grid, cudaStream_t st) {
     if (nper == 4 && npb == 1) return launch_split<4, 1>(p, smem, grid, st);
-    if (nper == 4 && npb == 2) return launch_split<4, 2>(p, smem, grid, st);
     if (nper == 8 && npb == 2) return launch_split<8, 2>(p, smem, grid, st);
-    if (nper == 8 && npb == 4) return launch_split<8, 4>(p, smem, grid, st);
     set_error("nms_frames: no two-array variant for %d + %d keys per lane", nper, npb);
     return VDET_ERR_UNSUPPORTED;
 }

@@ -42,10 +42,10 @@ __global__ void __launch_bounds__(256) spatial_maxpool_kernel(const BT* __restri
     for (int j = lane; j < n; j += 32) {
         const BT* b = det_boxes + (int64_t)(off + j) * 4;
         const double bx1 = (double)b[0], by1 = (double)b[1], bx2 = (double)b[2], by2 = (double)b[3];
-        const double ix1 = fmax(ax1, bx1), ix2 = fmin(ax2, bx2);
-        const double iy1 = fmax(ay1, by1), iy2 = fmin(ay2, by2);
-        const double iw = fmax(0.0, __dadd_rn(__dsub_rn(ix2, ix1), 1.0));
-        const double ih = fmax(0.0, __dadd_rn(__dsub_rn(iy2, iy1), 1.0));
+        const double ix1 = dmax_np(ax1, bx1), ix2 = dmin_np(ax2, bx2);
+        const double iy1 = dmax_np(ay1, by1), iy2 = dmin_np(ay2, by2);
+        const double iw = dmax_np(0.0, __dadd_rn(__dsub_rn(ix2, ix1), 1.0));
+        const double ih = dmax_np(0.0, __dadd_rn(__dsub_rn(iy2, iy1), 1.0));
         const double inter = __dmul_rn(iw, ih);
         const double ovr = __ddiv_rn(inter, __dsub_rn(__dadd_rn(aa, sm_area(bx1, by1, bx2, by2)), inter));
         if (mode == VDET_POOL_ARGMAX_SCORE) {
