@@ -569,6 +569,37 @@ def run_b200(args):
     res_reg = e2e_steps(last + 1)                               # ends on the shard the staged run ended on
     reg_ok = bool(np.array_equal(res_reg["keep_idx"], res["keep_idx"]) and np.array_equal(res_reg["succ"], res["succ"]))
     pp.pp.unregister_host_arrays()
+    # what the box allows for these byte counts with NO kernel at all, measured here on all ranks at once: (a) the
+    # upload alone from pinned buffers, (b) the staging copy of shard k+1 running beside the upload of shard k.  The
+    # staged path cannot beat (b), the registered / pinned paths cannot beat (a) (profiles/r02_scaling.md: the
+    # host side of these VMs saturates near 190 GB/s of DMA or 60 GB/s of staged uploads, whatever the rank count).
+    def ceiling(stage):
+        sl = pp.pp.slots
+        evs = [torch.cuda.Event(), torch.cuda.Event()]
+        reps = 24
+
+        def loop(n):
+            for k in range(n):
+                q = sl[k & 1]
+                if k >= 2:
+                    evs[k & 1].synchronize()
+                if stage:
+                    hb, hs = host_sets[k % NSETS]
+                    ops.host_copy_stream(q.h_boxes, hb.reshape(-1, 4), pp.pp.stage_threads)
+                    ops.host_copy_stream(q.h_scores, hs.reshape(-1, C), pp.pp.stage_threads)
+                with torch.cuda.stream(pp.pp.s_in):
+                    q.d_boxes.copy_(q.h_boxes, non_blocking=True)
+                    q.d_scores.copy_(q.h_scores, non_blocking=True)
+                    evs[k & 1].record(pp.pp.s_in)
+            torch.cuda.synchronize()
+        loop(6)
+        barrier()
+        t0 = time.perf_counter()
+        loop(reps)
+        dt = (time.perf_counter() - t0) * 1e3 / reps
+        barrier()
+        return max_over_ranks(dt)
+    ceil_h2d, ceil_stage = ceiling(False), ceiling(True)
     # the old definition, for comparison: the shard already sits in the pinned upload buffers and is re-submitted
     e2e_steps(2)                                                # both slots' pinned upload buffers hold a staged shard
     e2e_time(20, fresh=False)
@@ -588,6 +619,12 @@ def run_b200(args):
                                  "note": "same call, but the %d rotating caller arrays were pinned in place once with "
                                          "register_host_arrays(): a different shard every step, uploaded straight from the "
                                          "caller's memory (no staging copy: a third of the host-memory traffic)" % NSETS},
+           "box_ceiling": {"upload_only_ms": ceil_h2d, "stage_plus_upload_ms": ceil_stage,
+                           "e2e_vs_stage_plus_upload": ceil_stage / e2e_ms, "registered_vs_upload_only": ceil_h2d / reg_ms,
+                           "note": "the same %d bytes per rank and step moved with no kernel at all, all ranks at once: "
+                                   "pinned upload alone / staging copy of the next shard beside the upload (max over "
+                                   "ranks); ratios near 1 = the step runs at what the host side of the box delivers"
+                                   % pp.pp.h2d_bytes},
            "pinned_resubmit": {"ms_per_step": pinned_ms, "value": world * T * N / (pinned_ms / 1000.0),
                                "note": "round-1 definition: the same pre-pinned shard re-uploaded every step (no staging copy)"},
            "api": "vdetlib_b200.dist.ShardedVideoPostProcessor.submit_host(boxes, scores) / collect(ticket)"}
