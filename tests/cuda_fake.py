@@ -117,7 +117,7 @@ class FakeLib(object):
         return b""
 
 
-def link_frames(boxes, seg_offsets, max_seg_len, halo=None, halo_row_base=0, out=None, halo_count=None):
+def link_frames(boxes, seg_offsets, max_seg_len, halo=None, halo_row_base=0, out=None, halo_count=None, ws=None):
     """ops.link_frames on CPU tensors: FIRST arg-max IoU box of the next frame (halo for the last frame)."""
     b, off = boxes.numpy(), seg_offsets.numpy()
     n = b.shape[0]
@@ -168,6 +168,7 @@ def install(monkeypatch):
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
     monkeypatch.setattr(ops, "default_device", lambda: torch.device("cpu"))
     monkeypatch.setattr(ops, "link_frames", link_frames)
+    monkeypatch.setattr(ops, "link_workspace_bytes", lambda *a, **k: 64)
     real_load = _lib.load
 
     class _Both(object):                      # the real library for host-only entries, the fake for launches

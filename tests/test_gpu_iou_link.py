@@ -190,3 +190,50 @@ def test_follow_links_and_gather_rows():
         sflat = s.reshape(-1, C)
         ref = np.where(want.T[:, None, :] >= 0, sflat[np.maximum(want.T, 0)].transpose(0, 2, 1), np.float32(-1e5))
         assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("T,N,seed", [(6, 300, 1), (4, 64, 2), (3, 1000, 3), (3, 2000, 4), (5, 97, 5)])
+def test_x_sorted_link_equals_the_full_scan(T, N, seed):
+    """link_sorted.cu (frames sorted by x1, only the pairs that can overlap in x) against link.cu's full scan and the
+    C port: ragged frames, duplicated boxes (equal IoUs: the FIRST arg-max in original order must win), boxes that
+    touch nothing (successor = box 0, IoU 0), a halo with a device-side count, an insane box (falls back per pair)."""
+    rng = np.random.default_rng(seed)
+    dev = torch.device("cuda")
+    b, _ = synth.boxes_scores(T + 1, N, 1, seed=600 + seed)
+    counts = rng.integers(max(N // 2, 1), N + 1, T).astype(np.int32)
+    counts[rng.integers(0, T)] = N
+    for t in range(1, T):                                        # duplicates in the next frame -> tied IoUs
+        k = min(int(counts[t]) // 3, 40)
+        src = rng.integers(0, counts[t], k)
+        dst = rng.integers(0, counts[t], k)
+        b[t, dst] = b[t, src]
+    b[0, 0] = np.asarray([5000.0, 5000.0, 5010.0, 5010.0], np.float32)      # overlaps nothing
+    rows = np.concatenate([b[t, :counts[t]] for t in range(T)])
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    halo_cap = N
+    n_halo = int(rng.integers(1, N + 1))
+    halo = b[T, :halo_cap].copy()
+    d_rows, d_off = torch.from_numpy(rows).to(dev), torch.from_numpy(off).to(dev)
+    d_halo = torch.from_numpy(halo).to(dev)
+    d_cnt = torch.tensor([n_halo], dtype=torch.int32, device=dev)
+    for insane in (False, True):
+        if insane:
+            rows2 = rows.copy()
+            rows2[off[1] + 1] = np.asarray([10.0, 10.0, 9.0, 30.0], np.float32)      # zero width: not sane
+            d_rows = torch.from_numpy(rows2).to(dev)
+            frames = [rows2[off[t]:off[t + 1]] for t in range(T)]
+        else:
+            frames = [rows[off[t]:off[t + 1]] for t in range(T)]
+        s1, i1 = ops.link_frames(d_rows, d_off, N, d_halo, halo_row_base=len(rows), halo_count=d_cnt)
+        s0, i0 = ops.link_frames(d_rows, d_off, N, d_halo, halo_row_base=len(rows), halo_count=d_cnt, ws=False)
+        assert np.array_equal(s1.cpu().numpy(), s0.cpu().numpy()), insane
+        assert np.array_equal(i1.cpu().numpy().view(np.uint32), i0.cpu().numpy().view(np.uint32)), insane
+        if not insane:
+            su, io = s1.cpu().numpy(), i1.cpu().numpy()
+            for t in range(T):
+                nxt = frames[t + 1] if t + 1 < T else halo[:n_halo]
+                base = off[t + 1] if t + 1 < T else len(rows)
+                iou = c_oracle.pair_iou_f32(frames[t], nxt)
+                assert np.array_equal(su[off[t]:off[t + 1]], base + np.argmax(iou, axis=1)), t
+                assert np.array_equal(io[off[t]:off[t + 1]], iou.max(axis=1)), t
+            assert su[0] == off[1] and io[0] == 0.0                      # the far-away box: first box of the next frame

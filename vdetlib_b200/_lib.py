@@ -45,7 +45,8 @@ SIGNATURES = {
     "vdet_iou_matrix_f32": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "vdet_iou_matrix_f64": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "vdet_iou_bitmask_f32": (_i32, [_vp, _i32, _f64, _vp, _vp, _vp]),
-    "vdet_link_frames_f32": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _i64, _vp]),
+    "vdet_link_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "vdet_link_frames_f32": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _i64, _vp, _sz, _vp]),
     "vdet_spatial_maxpool": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _i64, _i32, _vp, _i32, _f64, _i32,
                                     _vp, _vp, _vp]),
     "vdet_score_completion_workspace_bytes": (_sz, [_i64, _i64, _i32]),

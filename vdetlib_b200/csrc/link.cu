@@ -13,6 +13,8 @@
 // (best, arg) per row.  Rows per CTA (THREADS x ROWS) are chosen per launch so that a frame pads
 // to as few row slots as possible and, among equals, is staged by as few CTAs as possible: a
 // 2000-box frame is staged by 4 CTAs (512 rows each) instead of 32.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vdet {
@@ -153,19 +155,36 @@ static int launch_link(const float* boxes, const int32_t* seg_offsets, int n_seg
     return VDET_OK;
 }
 
+// link_sorted.cu: the same link with the pairs that cannot overlap in x left out (frames of up to 2048 boxes)
+size_t link_sorted_ws_bytes(int64_t n_rows, int n_segs, int n_halo);
+int launch_link_frames_sorted(const float* boxes, const int32_t* seg_offsets, int n_segs, int max_seg_len,
+                              const float* halo_boxes, int n_halo, const int32_t* n_halo_dev, int halo_row_base,
+                              int32_t* succ, float* best_iou, int64_t n_rows, void* ws, cudaStream_t st);
+
 }  // namespace vdet
 
 using namespace vdet;
 
+extern "C" size_t vdet_link_workspace_bytes(int64_t n_rows, int n_segs, int n_halo) {
+    return link_sorted_ws_bytes(n_rows > 0 ? n_rows : 0, n_segs > 0 ? n_segs : 0, n_halo > 0 ? n_halo : 0);
+}
+
 extern "C" int vdet_link_frames_f32(const float* boxes, const int32_t* seg_offsets, int n_segs,
                                     int max_seg_len, const float* halo_boxes, int n_halo,
                                     const int32_t* n_halo_dev, int halo_row_base,
-                                    int32_t* succ, float* best_iou, int64_t n_rows, void* stream) {
+                                    int32_t* succ, float* best_iou, int64_t n_rows,
+                                    void* ws, size_t ws_bytes, void* stream) {
     VDET_REQUIRE(n_segs >= 0 && max_seg_len >= 0 && n_halo >= 0 && n_rows >= 0, "link_frames: negative size");
     if (n_segs == 0 || n_rows == 0 || max_seg_len == 0) return VDET_OK;
     VDET_REQUIRE(((uintptr_t)boxes & 15) == 0 && ((uintptr_t)halo_boxes & 15) == 0,
                  "link_frames: boxes must be 16-byte aligned");
     VDET_REQUIRE(max_seg_len <= 65535 * 64, "link_frames: frame too long");
+    // with a workspace: x1-sorted frames, only the pairs that can overlap in x are evaluated (same results)
+    static const bool no_sort = getenv("VDET_LINK_NO_SORT") != nullptr && atoi(getenv("VDET_LINK_NO_SORT")) != 0;
+    if (ws != nullptr && !no_sort && max_seg_len <= 2048 && n_halo <= 2048 && max_seg_len >= 64 &&
+        ws_bytes >= link_sorted_ws_bytes(n_rows, n_segs, halo_boxes ? n_halo : 0))
+        return launch_link_frames_sorted(boxes, seg_offsets, n_segs, max_seg_len, halo_boxes, halo_boxes ? n_halo : 0,
+                                         n_halo_dev, halo_row_base, succ, best_iou, n_rows, ws, (cudaStream_t)stream);
     // rows per CTA: fewest padded row slots, then fewest CTAs per frame
     const int cand[4] = {64, 128, 256, 512};
     int best_rpc = 64;

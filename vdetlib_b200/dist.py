@@ -142,7 +142,7 @@ class ShardedVideoPostProcessor(object):
                              status=pp.status, frame_major_out=True, out=(pp.d_idx, pp.d_cnt, pp.d_mask))
         main.wait_stream(self.side)
         succ, link_iou = ops.link_frames(d_boxes, pp.seg_offsets, pp.N, halo, halo_row_base=pp.T * pp.N,
-                                         out=(pp.d_succ, pp.d_iou), halo_count=halo_count)
+                                         out=(pp.d_succ, pp.d_iou), halo_count=halo_count, ws=pp.slots[0].link_ws)
         res = pp._views(out)
         res.update(succ=succ, link_iou=link_iou)
         return res

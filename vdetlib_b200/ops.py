@@ -270,13 +270,15 @@ def iou_bitmask(boxes, thresh, status=None):
     return mask, status
 
 
-def link_frames(boxes, seg_offsets, max_seg_len, halo=None, halo_row_base=0, out=None, halo_count=None):
+def link_frames(boxes, seg_offsets, max_seg_len, halo=None, halo_row_base=0, out=None, halo_count=None, ws=None):
     """Frame-to-frame link: for each box, the FIRST arg-max IoU box of the next frame.
     Returns (succ i32 [n] packed row of the successor / halo_row_base + halo index / -1,
     best_iou f32 [n]).  ``out=(succ, best_iou)`` writes into caller-provided buffers.
     ``halo_count``: optional int32 CUDA tensor [1] with the halo's box count (``halo`` is then a
     buffer of that capacity; ragged shards learn the count from the boundary exchange).
-    A shard passes ``halo_row_base = n`` so that halo successors are >= n (see follow_links)."""
+    A shard passes ``halo_row_base = n`` so that halo successors are >= n (see follow_links).
+    ``ws``: uint8 CUDA workspace (``link_workspace_bytes``) for the x-sorted variant; by default one is taken from
+    the per-stream cache -- callers that capture the call in a CUDA graph pass their own, fixed buffer."""
     lib = _lib.load()
     _need(boxes, "boxes", torch.float32, 2)
     _need(seg_offsets, "seg_offsets", torch.int32, 1)
@@ -294,11 +296,20 @@ def link_frames(boxes, seg_offsets, max_seg_len, halo=None, halo_row_base=0, out
         n_halo = halo.shape[0]
     if halo_count is not None:
         _need(halo_count, "halo_count", torch.int32)
-    rc = lib.vdet_link_frames_f32(_ptr(boxes), _ptr(seg_offsets), seg_offsets.numel() - 1, int(max_seg_len),
+    S = seg_offsets.numel() - 1
+    if ws is None:
+        ws = _workspace(lib.vdet_link_workspace_bytes(n, S, n_halo), boxes.device)
+    elif ws is False:                     # the full N x M scan (no x-sorting): what the sorted variant must equal
+        ws = None
+    rc = lib.vdet_link_frames_f32(_ptr(boxes), _ptr(seg_offsets), S, int(max_seg_len),
                                   _ptr(halo), n_halo, _ptr(halo_count), int(halo_row_base), _ptr(succ), _ptr(best),
-                                  n, _stream())
+                                  n, _ptr(ws), ws.numel() if ws is not None else 0, _stream())
     _lib.check(rc, "link_frames")
     return succ, best
+
+
+def link_workspace_bytes(n_rows, n_segs, n_halo=0):
+    return int(_lib.load().vdet_link_workspace_bytes(int(n_rows), int(n_segs), int(n_halo)))
 
 
 def spatial_maxpool(tub_boxes, tub_seg, det_boxes, det_scores, det_seg_offsets, thresh=0.7,

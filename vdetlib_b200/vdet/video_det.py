@@ -125,6 +125,8 @@ class _Slot(object):
         self.ws_bytes = _lib.load().vdet_nms_frames_workspace_bytes(N, C, dev.index or 0) if N > 1024 else 0
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev) if self.ws_bytes else None
         self.ev_in = [torch.cuda.Event() for _ in range(pp.n_chunks)]
+        # fixed workspace of the x-sorted link (its address is baked into the slot's CUDA graphs)
+        self.link_ws = torch.empty(ops.link_workspace_bytes(rows, T, N), dtype=torch.uint8, device=dev)
 
 
 class VideoPostProcessor(object):
@@ -235,7 +237,7 @@ class VideoPostProcessor(object):
         out = ops.nms_frames(d_boxes, d_scores, self.seg_offsets, self.nms_thresh, self.N, want_mask=True,
                              status=self.status, frame_major_out=True, out=(self.d_idx, self.d_cnt, self.d_mask))
         ops.link_frames(d_boxes, self.seg_offsets, self.N, halo, halo_row_base=self.T * self.N,
-                        out=(self.d_succ, self.d_iou), halo_count=halo_count)
+                        out=(self.d_succ, self.d_iou), halo_count=halo_count, ws=self.slots[0].link_ws)
         return out
 
     def run_device(self, d_boxes, d_scores, halo=None, graph=False):
@@ -374,7 +376,7 @@ class VideoPostProcessor(object):
         cur.wait_event(sl.ev_boxes)
         seg = sl.d_seg[:n_frames + 1]
         ops.link_frames(sl.d_boxes[:rows], seg, N, halo, halo_row_base=rows, out=(sl.d_succ, sl.d_iou),
-                        halo_count=halo_count)
+                        halo_count=halo_count, ws=sl.link_ws)
         sl.ev_link.record(cur)
         s_out.wait_event(sl.ev_link)
         with torch.cuda.stream(s_out):
