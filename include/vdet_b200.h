@@ -213,8 +213,8 @@ int vdet_iou_bitmask_f32(const float* boxes, int n, double thresh, uint32_t* mas
  * (succ >= n_rows = "continues on the next shard") instead of aliasing them.
  * n_halo_dev (optional, device): the halo's box count when only the device knows it (ragged
  * frames: it arrives with the boundary all-gather); n_halo is then the capacity of halo_boxes.
- * ws (optional, vdet_link_workspace_bytes): with a workspace and frames of 64..2048 boxes every frame
- * is sorted by x1 first and only the pairs that can overlap in x are evaluated -- about a third of
+ * ws (optional, vdet_link_workspace_bytes): with a workspace and frames of 512..2048 boxes every frame
+ * is sorted by x1 first and only the pairs that can overlap in x are evaluated -- about half of
  * them on BASELINE's synthetic frames, same results bit for bit; without one, every pair is.
  * ------------------------------------------------------------------------------------- */
 size_t vdet_link_workspace_bytes(int64_t n_rows, int n_segs, int n_halo);
@@ -255,6 +255,14 @@ size_t vdet_score_completion_workspace_bytes(int64_t n_rows, int64_t L, int dtyp
 int vdet_score_completion(void* scores, int dtype, int64_t n_rows, int64_t L, int64_t ld,
                           const int32_t* lengths, double miss_thr, uint32_t* status,
                           void* ws, size_t ws_bytes, void* stream);
+/* The same for rows that are ONE FRAME RANGE of longer tubelets (frame-sharded completion): a run that
+ * touches the shard's first / last column is completed from the nearest valid score of the neighbouring shards.
+ *   bounds [n_rows, 4] (row dtype): left gap, left value, right gap, right value; gap = number of (missing)
+ *   frames between that score and this shard's first / last column, < 0 = no valid score on that side.
+ * A row with no valid score anywhere (both gaps < 0, nothing valid inside) sets VDET_STATUS_ALL_MISSING. */
+int vdet_score_completion_bounded(void* scores, int dtype, int64_t n_rows, int64_t L, int64_t ld,
+                                  const int32_t* lengths, double miss_thr, const void* bounds,
+                                  uint32_t* status, void* ws, size_t ws_bytes, void* stream);
 int vdet_temporal_maxpool(const void* scores, void* out, int dtype, int64_t n_rows, int64_t L,
                           int64_t ld, const int32_t* lengths, int window, double pad, void* stream);
 int vdet_temporal_conv1d(const void* x, void* out, int dtype, int64_t n_rows, int64_t L,

@@ -136,7 +136,26 @@ def spatial_maxpool(tub_boxes, tub_seg, det_boxes, det_scores, det_seg_offsets, 
     return torch.from_numpy(arg), torch.from_numpy(score)
 
 
-def score_completion_(scores, lengths=None, miss_thr=-10.0, status=None):
+def _completion_row_bounded(row, bnd, miss_thr):
+    """A row that is one frame range of a longer tubelet: rebuild the part of the tubelet that matters (the nearest
+    valid score on either side at its true distance, missing frames in between), complete it with the reference's
+    loop and cut the range out again."""
+    lg, lv, rg, rv = (float(x) for x in bnd)
+    left = ([lv] + [MISSING] * int(lg)) if lg >= 0 else []
+    right = ([MISSING] * int(rg) + [rv]) if rg >= 0 else []
+    full = oracle_np.completion_row(np.concatenate([left, row, right]), miss_thr)
+    return full[len(left):len(left) + len(row)]
+
+
+def score_completion_(scores, lengths=None, miss_thr=-10.0, status=None, bounds=None):
+    if bounds is not None:
+        a, st = scores.numpy(), 0
+        for i in range(a.shape[0]):
+            try:
+                a[i] = _completion_row_bounded(a[i].astype(np.float64), bounds[i].numpy(), miss_thr).astype(a.dtype)
+            except IndexError:
+                st |= 2
+        return torch.tensor([st], dtype=torch.int32)
     a = scores.numpy()
     lens = lengths.numpy() if lengths is not None else np.full(a.shape[0], a.shape[1])
     st = 0

@@ -78,3 +78,9 @@ def test_round2_call_sites_golden():
     G_tub.test_score_conv_cls_channel_marshalling_golden()
     G_tub.test_score_conv_cls_temporal_conv_net_batched()
     G_tub.test_threshold_topk_pinned_to_fast_rcnn_det_vid()
+
+
+def test_bounded_completion_on_the_double():
+    """The assertions of the GPU test of vdet_score_completion_bounded with the oracle-backed stand-in: checks the
+    test's own bounds bookkeeping (and the stand-in) against whole-row completion."""
+    G_tub.test_bounded_completion_equals_the_unsharded_rows(np.float64)

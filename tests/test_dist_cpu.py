@@ -135,6 +135,57 @@ def test_temporal_sharding_single_process():
         frame_sharded_window_op(torch.from_numpy(rows[:, :2]), 3, maxpool, pad_value=-1e5)
 
 
+def _completion_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import kernel_double
+    from oracle import oracle_np
+    from vdetlib_b200 import ops
+    from vdetlib_b200.dist import frame_sharded_completion_, shard_range
+    ops.score_completion_ = kernel_double.score_completion_              # the kernel's stand-in on CPU tensors
+    rng = np.random.default_rng(3)
+    rows = rng.uniform(0, 1, (9, 47))                                    # every rank knows the whole block, for checking
+    for r in range(9):
+        for _ in range(6):
+            a = rng.integers(0, 47)
+            rows[r, a:a + rng.integers(1, 14)] = -1e5
+    rows[1, :] = -1e5; rows[1, 20] = 0.25                                # one valid score: every shard but one is empty
+    rows[2, :30] = -1e5                                                  # a leading run over several shards
+    rows[3, 10:] = -1e5                                                  # a trailing run over several shards
+    rows[4, :] = -1e5                                                    # no valid score at all -> IndexError / status 2
+    want = []
+    for r in rows:
+        try:
+            want.append(oracle_np.completion_row(r))
+        except IndexError:
+            want.append(None)
+    a, b = shard_range(rows.shape[1], world, rank)
+    local = torch.from_numpy(rows[:, a:b].copy())
+    status = frame_sharded_completion_(local, -10.0)
+    ok = bool(int(status[0]) & 2)                                        # row 4
+    for r in range(9):
+        if want[r] is not None:
+            ok = ok and np.array_equal(local.numpy()[r], want[r][a:b])
+    with open(os.path.join(out_dir, "rank%d" % rank), "w") as f:
+        f.write("ok" if ok else "bad")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_frame_sharded_completion_gloo(tmp_path, world):
+    """Score completion of rows sharded by frame: a 4-value summary per (row, rank) is all-gathered, every
+    rank completes its columns with the positions of the whole tubelet; runs that span one or several shard
+    boundaries, shards without any valid score, all-missing rows.  Equal to the unsharded rows bit for bit."""
+    port = _free_port()
+    mp.spawn(_completion_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(os.path.join(str(tmp_path), "rank%d" % r)).read() == "ok"
+
+
 def _vid_nms_worker(rank, world, port, out_dir):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"

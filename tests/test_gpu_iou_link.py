@@ -192,7 +192,7 @@ def test_follow_links_and_gather_rows():
         assert np.array_equal(out, ref)
 
 
-@pytest.mark.parametrize("T,N,seed", [(6, 300, 1), (4, 64, 2), (3, 1000, 3), (3, 2000, 4), (5, 97, 5)])
+@pytest.mark.parametrize("T,N,seed", [(6, 300, 1), (4, 512, 2), (3, 1000, 3), (3, 2000, 4), (5, 640, 5), (3, 2048, 6)])
 def test_x_sorted_link_equals_the_full_scan(T, N, seed):
     """link_sorted.cu (frames sorted by x1, only the pairs that can overlap in x) against link.cu's full scan and the
     C port: ragged frames, duplicated boxes (equal IoUs: the FIRST arg-max in original order must win), boxes that

@@ -398,3 +398,35 @@ def test_threshold_topk_pinned_to_fast_rcnn_det_vid():
             assert np.array_equal(got[j][0], want), (t, j)
             assert np.array_equal(want_np[j], want), (t, j)
         assert any(len(g["all_boxes"][j][t]) == 100 for j in range(1, scores.shape[1]))     # the cap was hit
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_bounded_completion_equals_the_unsharded_rows(dtype):
+    """vdet_score_completion_bounded: rows cut into frame ranges ("virtual shards" on one GPU), each completed with the
+    nearest valid scores of its neighbours as (gap, value) bounds -- the same bits as completing the whole rows."""
+    rng = np.random.default_rng(8)
+    rows = synth.score_rows(40, 600, seed=8, missing_frac=0.25, dtype=dtype, max_run=60)
+    rows[3, :] = -1e5; rows[3, 411] = 0.5
+    rows[5, :350] = -1e5
+    rows[6, 100:] = -1e5
+    dev = ops.default_device()
+    whole = torch.from_numpy(rows.copy()).to(dev)
+    ops.raise_for_status(ops.score_completion_(whole))
+    want = whole.cpu().numpy()
+    edges = [0, 97, 98, 300, 431, 600]
+    for a, b in zip(edges[:-1], edges[1:]):
+        bounds = np.full((rows.shape[0], 4), -1.0, dtype)
+        for r in range(rows.shape[0]):
+            lv = np.nonzero(rows[r, :a] > -10)[0]
+            rv = np.nonzero(rows[r, b:] > -10)[0]
+            if len(lv):
+                bounds[r, 0], bounds[r, 1] = a - 1 - lv[-1], rows[r, lv[-1]]
+            if len(rv):
+                bounds[r, 2], bounds[r, 3] = rv[0], rows[r, b + rv[0]]
+        part = torch.from_numpy(rows[:, a:b].copy()).to(dev)
+        ops.raise_for_status(ops.score_completion_(part, bounds=torch.from_numpy(bounds).to(dev)))
+        assert np.array_equal(part.cpu().numpy(), want[:, a:b]), (a, b)
+    # a range with no valid score on either side and none inside: IndexError like the reference
+    part = torch.full((2, 50), -1e5, dtype=torch.from_numpy(rows).dtype, device=dev)
+    with pytest.raises(IndexError):
+        ops.raise_for_status(ops.score_completion_(part, bounds=torch.full((2, 4), -1.0, dtype=part.dtype, device=dev)))

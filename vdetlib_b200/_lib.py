@@ -51,6 +51,7 @@ SIGNATURES = {
                                     _vp, _vp, _vp]),
     "vdet_score_completion_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "vdet_score_completion": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _f64, _vp, _vp, _sz, _vp]),
+    "vdet_score_completion_bounded": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _f64, _vp, _vp, _vp, _sz, _vp]),
     "vdet_temporal_maxpool": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _i32, _f64, _vp]),
     "vdet_temporal_conv1d": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _vp]),
     "vdet_tubelet_interpolate_f64": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp]),

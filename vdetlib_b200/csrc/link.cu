@@ -181,7 +181,9 @@ extern "C" int vdet_link_frames_f32(const float* boxes, const int32_t* seg_offse
     VDET_REQUIRE(max_seg_len <= 65535 * 64, "link_frames: frame too long");
     // with a workspace: x1-sorted frames, only the pairs that can overlap in x are evaluated (same results)
     static const bool no_sort = getenv("VDET_LINK_NO_SORT") != nullptr && atoi(getenv("VDET_LINK_NO_SORT")) != 0;
-    if (ws != nullptr && !no_sort && max_seg_len <= 2048 && n_halo <= 2048 && max_seg_len >= 64 &&
+    // (measured: 2500 x 1000 boxes 1.83 -> 1.11 ms, 500 x 2000 boxes 1.53 -> 0.88 ms; at 300 boxes per frame a warp's rows
+    // span most of the frame in x and sorting only breaks even, so short frames keep the plain scan)
+    if (ws != nullptr && !no_sort && max_seg_len <= 2048 && n_halo <= 2048 && max_seg_len >= 512 &&
         ws_bytes >= link_sorted_ws_bytes(n_rows, n_segs, halo_boxes ? n_halo : 0))
         return launch_link_frames_sorted(boxes, seg_offsets, n_segs, max_seg_len, halo_boxes, halo_boxes ? n_halo : 0,
                                          n_halo_dev, halo_row_base, succ, best_iou, n_rows, ws, (cudaStream_t)stream);

@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(256) completion_fill_kernel(T* __restrict__ sc
                                                               const int32_t* __restrict__ lengths,
                                                               int words_per_row, int64_t n_words,
                                                               const uint32_t* __restrict__ bitmap,
+                                                              const T* __restrict__ bounds,
                                                               uint32_t* status) {
     const int64_t wid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (wid >= n_words) return;
@@ -209,17 +210,25 @@ __global__ void __launch_bounds__(256) completion_fill_kernel(T* __restrict__ sc
             }
             if (j > len) j = len;
         }
-        if (i == 0) {
-            if (j >= len) { atomicOr(status, VDET_STATUS_ALL_MISSING); continue; }     // tubelet_cls.py:295 IndexError
-            const T r = g[j];
+        // the valid neighbours of the run: inside the row, or -- for a row that is one frame range of a longer
+        // tubelet (frame-sharded completion) -- the nearest valid score of the neighbouring shards, given as
+        // bounds[row] = (left gap, left value, right gap, right value): gap = missing frames between that score
+        // and this shard's first / last column, < 0 = there is none.  Positions are those of the whole tubelet.
+        bool has_l = i > 0, has_r = j < len;
+        T l = (T)0, r = (T)0;
+        int i_eff = i, j_eff = j;
+        if (has_l) l = g[i - 1];
+        else if (bounds != nullptr && bounds[row * 4 + 0] >= (T)0) { has_l = true; l = bounds[row * 4 + 1]; i_eff = -(int)bounds[row * 4 + 0]; }
+        if (has_r) r = g[j];
+        else if (bounds != nullptr && bounds[row * 4 + 2] >= (T)0) { has_r = true; r = bounds[row * 4 + 3]; j_eff = len + (int)bounds[row * 4 + 2]; }
+        if (!has_l) {
+            if (!has_r) { atomicOr(status, VDET_STATUS_ALL_MISSING); continue; }     // tubelet_cls.py:295 IndexError
             for (int k = i; k < j; ++k) g[k] = r;
-        } else if (j >= len) {
-            const T l = g[i - 1];
+        } else if (!has_r) {
             for (int k = i; k < j; ++k) g[k] = l;
         } else {
-            const T l = g[i - 1], r = g[j];
-            const T d = t_sub(r, l), den = (T)(j - i + 1);
-            for (int k = i; k < j; ++k) g[k] = t_add(l, t_div(t_mul(d, (T)(k - i + 1)), den));
+            const T d = t_sub(r, l), den = (T)(j_eff - i_eff + 1);
+            for (int k = i; k < j; ++k) g[k] = t_add(l, t_div(t_mul(d, (T)(k - i_eff + 1)), den));
         }
     }
 }
@@ -385,7 +394,7 @@ static inline size_t completion_bitmap_words(int64_t n_rows, int64_t L) {
 
 template <typename T>
 static int run_completion(void* scores, int64_t n_rows, int64_t L, int64_t ld, const int32_t* lengths,
-                          double miss_thr, uint32_t* status, void* ws, size_t ws_bytes, cudaStream_t st) {
+                          double miss_thr, const void* bounds, uint32_t* status, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (L >= 0x7fffffff - 1024) { set_error("score_completion: too large"); return VDET_ERR_UNSUPPORTED; }
     const int words_per_row = (int)((L + 31) / 32);
     const int spans_per_row = (words_per_row + 31) / 32;
@@ -404,7 +413,7 @@ static int run_completion(void* scores, int64_t n_rows, int64_t L, int64_t ld, c
                                                                         spans_per_row, n_spans, (T)miss_thr, bitmap);
     VDET_LAUNCH_CHECK();
     completion_fill_kernel<T><<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>((T*)scores, L, ld, lengths, words_per_row,
-                                                                                 n_words, bitmap, status);
+                                                                                 n_words, bitmap, (const T*)bounds, status);
     VDET_LAUNCH_CHECK();
     return VDET_OK;
 }
@@ -426,8 +435,20 @@ extern "C" int vdet_score_completion(void* scores, int dtype, int64_t n_rows, in
     VDET_REQUIRE(status != nullptr, "score_completion: null status");
     if (n_rows == 0 || L == 0) return VDET_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    return dtype == VDET_DTYPE_F32 ? run_completion<float>(scores, n_rows, L, ld, lengths, miss_thr, status, ws, ws_bytes, st)
-                                   : run_completion<double>(scores, n_rows, L, ld, lengths, miss_thr, status, ws, ws_bytes, st);
+    return dtype == VDET_DTYPE_F32 ? run_completion<float>(scores, n_rows, L, ld, lengths, miss_thr, nullptr, status, ws, ws_bytes, st)
+                                   : run_completion<double>(scores, n_rows, L, ld, lengths, miss_thr, nullptr, status, ws, ws_bytes, st);
+}
+
+extern "C" int vdet_score_completion_bounded(void* scores, int dtype, int64_t n_rows, int64_t L, int64_t ld,
+                                             const int32_t* lengths, double miss_thr, const void* bounds,
+                                             uint32_t* status, void* ws, size_t ws_bytes, void* stream) {
+    VDET_REQUIRE(n_rows >= 0 && L >= 0 && ld >= L, "score_completion: bad shape");
+    VDET_REQUIRE(dtype == VDET_DTYPE_F32 || dtype == VDET_DTYPE_F64, "score_completion: bad dtype");
+    VDET_REQUIRE(status != nullptr && bounds != nullptr, "score_completion_bounded: null status / bounds");
+    if (n_rows == 0 || L == 0) return VDET_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    return dtype == VDET_DTYPE_F32 ? run_completion<float>(scores, n_rows, L, ld, lengths, miss_thr, bounds, status, ws, ws_bytes, st)
+                                   : run_completion<double>(scores, n_rows, L, ld, lengths, miss_thr, bounds, status, ws, ws_bytes, st);
 }
 
 extern "C" int vdet_temporal_maxpool(const void* scores, void* out, int dtype, int64_t n_rows, int64_t L,

@@ -279,3 +279,54 @@ def frame_sharded_window_op(local_cols, half_window, op, pad_value=None, group=N
     right = recv[rank + 1][:, :h] if rank < world - 1 else outside(local_cols[:, L - 1:])
     ext = torch.cat([left, local_cols, right], dim=1).contiguous()
     return op(ext)[:, h:h + L]
+
+
+def frame_sharded_completion_(local_cols, miss_thr=-10.0, group=None, status=None):
+    """do_score_completion (vdet/tubelet_cls.py:284-303) for rows sharded BY FRAME: every rank holds the
+    columns (frames) [f0, f1) of ALL rows, in place.  A run of missing scores that touches a shard edge is completed
+    from the nearest valid score on the other side of it, which may be several ranks away: one all-gather of a
+    4-value summary per (row, rank) -- first valid column + value, last valid column + value -- and of the shard
+    widths gives every rank the (gap, value) pair it needs on each side; the kernel then works with the positions
+    of the whole tubelet (``vdet_score_completion_bounded``).  Bit-identical to completing the unsharded rows."""
+    from . import ops
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    rows, L = local_cols.shape
+    dt = local_cols.dtype
+    valid = local_cols > miss_thr                                   # missing: score <= miss_thr (:286)
+    any_valid = valid.any(dim=1)
+    idx = torch.arange(L, device=local_cols.device)
+    first = torch.where(valid, idx, torch.full_like(idx, L)).min(dim=1).values if L else torch.zeros(rows, dtype=torch.long, device=local_cols.device)
+    last = torch.where(valid, idx, torch.full_like(idx, -1)).max(dim=1).values if L else torch.full((rows,), -1, dtype=torch.long, device=local_cols.device)
+    safe_first, safe_last = first.clamp(max=max(L - 1, 0)), last.clamp(min=0)
+    summ = torch.stack([torch.where(any_valid, first, torch.full_like(first, -1)).to(torch.float64),
+                        local_cols.gather(1, safe_first[:, None])[:, 0].to(torch.float64) if L else torch.zeros(rows, dtype=torch.float64, device=local_cols.device),
+                        torch.where(any_valid, last, torch.full_like(last, -1)).to(torch.float64),
+                        local_cols.gather(1, safe_last[:, None])[:, 0].to(torch.float64) if L else torch.zeros(rows, dtype=torch.float64, device=local_cols.device),
+                        torch.full((rows,), float(L), dtype=torch.float64, device=local_cols.device)], dim=1).contiguous()
+    if world > 1:
+        allsum = summ.new_empty((world, rows, 5))
+        dist.all_gather_into_tensor(allsum.view(world * rows, 5), summ, group=group)
+    else:
+        allsum = summ.unsqueeze(0)
+    bounds = torch.full((rows, 4), -1.0, dtype=torch.float64, device=local_cols.device)
+    # nearest valid score to the left: walk the ranks below this one, accumulating the frames in between
+    gap = torch.zeros(rows, dtype=torch.float64, device=local_cols.device)
+    found = torch.zeros(rows, dtype=torch.bool, device=local_cols.device)
+    for r in range(rank - 1, -1, -1):
+        s_r = allsum[r]
+        has = (s_r[:, 2] >= 0) & ~found
+        bounds[:, 0] = torch.where(has, gap + (s_r[:, 4] - 1 - s_r[:, 2]), bounds[:, 0])
+        bounds[:, 1] = torch.where(has, s_r[:, 3], bounds[:, 1])
+        found |= has
+        gap = gap + s_r[:, 4]
+    gap = torch.zeros(rows, dtype=torch.float64, device=local_cols.device)
+    found = torch.zeros(rows, dtype=torch.bool, device=local_cols.device)
+    for r in range(rank + 1, world):
+        s_r = allsum[r]
+        has = (s_r[:, 0] >= 0) & ~found
+        bounds[:, 2] = torch.where(has, gap + s_r[:, 0], bounds[:, 2])
+        bounds[:, 3] = torch.where(has, s_r[:, 1], bounds[:, 3])
+        found |= has
+        gap = gap + s_r[:, 4]
+    return ops.score_completion_(local_cols, None, miss_thr, status, bounds=bounds.to(dt))

@@ -349,14 +349,26 @@ def _rows(x, name):
     return _lib.DTYPE_F32 if x.dtype == torch.float32 else _lib.DTYPE_F64
 
 
-def score_completion_(scores, lengths=None, miss_thr=-10.0, status=None):
-    """do_score_completion (vdet/tubelet_cls.py:284-303) on [rows, L] score rows, IN PLACE."""
+def score_completion_(scores, lengths=None, miss_thr=-10.0, status=None, bounds=None):
+    """do_score_completion (vdet/tubelet_cls.py:284-303) on [rows, L] score rows, IN PLACE.
+    ``bounds`` [rows, 4] (same dtype): for rows that are one frame range of longer tubelets, the nearest valid score
+    of the neighbouring shards as (left gap, left value, right gap, right value), gap < 0 = none (see dist.py)."""
     lib = _lib.load()
     dt = _rows(scores, "scores")
     if status is None:
         status = new_status(scores.device)
     ws_bytes = lib.vdet_score_completion_workspace_bytes(scores.shape[0], scores.shape[1], dt)
     ws = _workspace(ws_bytes, scores.device)
+    if bounds is not None:
+        _need(bounds, "bounds", scores.dtype, 2)
+        if tuple(bounds.shape) != (scores.shape[0], 4):
+            raise ValueError("score_completion_: bounds must be [rows, 4]")
+        bounds = bounds.contiguous()
+        rc = lib.vdet_score_completion_bounded(_ptr(scores), dt, scores.shape[0], scores.shape[1], scores.stride(0),
+                                               _ptr(lengths), float(miss_thr), _ptr(bounds), _ptr(status), _ptr(ws),
+                                               ws_bytes, _stream())
+        _lib.check(rc, "score_completion")
+        return status
     rc = lib.vdet_score_completion(_ptr(scores), dt, scores.shape[0], scores.shape[1], scores.stride(0),
                                    _ptr(lengths), float(miss_thr), _ptr(status), _ptr(ws), ws_bytes, _stream())
     _lib.check(rc, "score_completion")
