@@ -429,7 +429,11 @@ def run_b200(args):
         b, s = synth.boxes_scores(T, N, C, seed=shard_seed(rank, k))
         host_sets.append((b, s))
         sets.append((torch.from_numpy(b.reshape(-1, 4)).to(dev), torch.from_numpy(s.reshape(-1, C)).to(dev)))
-    pp = ShardedVideoPostProcessor(T, N, C, NMS_THRESH, dev, bind_cpus=(world > 1))
+    # steps in flight (VDET_E2E_SLOTS): measured 1.07 / 1.09 / 1.01 ms per step with 2 / 3 / 4 -- with more than two the
+    # host never waits in collect(), but its staging copy then always runs beside an upload and slows down by what the
+    # wait was (0.72 -> 0.90 ms): the step is bound by host memory bandwidth either way
+    n_slots = int(os.environ.get("VDET_E2E_SLOTS", "2"))
+    pp = ShardedVideoPostProcessor(T, N, C, NMS_THRESH, dev, bind_cpus=(world > 1), n_slots=n_slots)
     seg = pp.pp.seg_offsets
 
     for k in range(W):
@@ -507,8 +511,8 @@ def run_b200(args):
 
     # ---- e2e: the user's call.  Every step takes a DIFFERENT shard from ordinary (pageable) NumPy arrays: the
     # caller's memory is streamed into the slot's pinned upload buffers (inside the timed region), uploaded,
-    # processed, and the ordered keep lists of every (frame, class) + the link come back to host memory.  Two steps
-    # are in flight (submit k+1, then collect k).  The host<->device link of these boxes ramps up under sustained
+    # processed, and the ordered keep lists of every (frame, class) + the link come back to host memory.  n_slots steps
+    # are in flight (the oldest is collected when every slot is busy).  The host<->device link of these boxes ramps up under sustained
     # DMA traffic (profiles/r01_pcie.md), so the warm-up runs until the step time stops improving (bounded;
     # the count is reported as e2e.warmup_steps), then exactly K steps are timed.
     use_graph = os.environ.get("VDET_E2E_GRAPH", "1") != "0"
@@ -519,14 +523,15 @@ def run_b200(args):
             if fresh:
                 return pp.submit_host(*host_sets[k % NSETS], graph=use_graph)
             return pp.submit_staged(graph=use_graph)
-        t = submit(0)
-        for k in range(1, n):
-            t2 = submit(k)
+        tickets, r = [], None
+        for k in range(n):
+            if len(tickets) == n_slots:                            # every slot in flight: take the oldest result home
+                r = pp.collect(tickets.pop(0))
+                consumed[0] += int(r["keep_off"][-1])              # the host reads the result it was handed
+            tickets.append(submit(k))
+        for t in tickets:
             r = pp.collect(t)
-            consumed[0] += int(r["keep_off"][-1])                   # the host reads the result it was handed
-            t = t2
-        r = pp.collect(t)
-        consumed[0] += int(r["keep_off"][-1])
+            consumed[0] += int(r["keep_off"][-1])
         return r
 
     def e2e_time(n, fresh=True):
@@ -601,7 +606,7 @@ def run_b200(args):
         return max_over_ranks(dt)
     ceil_h2d, ceil_stage = ceiling(False), ceiling(True)
     # the old definition, for comparison: the shard already sits in the pinned upload buffers and is re-submitted
-    e2e_steps(2)                                                # both slots' pinned upload buffers hold a staged shard
+    e2e_steps(n_slots)                                          # every slot's pinned upload buffers hold a staged shard
     e2e_time(20, fresh=False)
     pinned_ms = e2e_time(max(K, 20), fresh=False)
     e2e = {"value": world * T * N / (e2e_ms / 1000.0), "unit": "boxes/s", "ms_per_step": e2e_ms,
@@ -612,7 +617,7 @@ def run_b200(args):
                     "pinned upload buffers (%d host threads) is inside the timed region" % (NSETS, pp.pp.stage_threads or 8),
            "output": "ordered keep lists of every (frame, class) (uint16 index within the frame, utils/nms.pyx:43-66 "
                      "order) + prefix offsets + succ + link_iou, in host memory",
-           "graph": use_graph, "steps_in_flight": 2,
+           "graph": use_graph, "steps_in_flight": n_slots,
            "warmup_steps": e2e_warm, "warmup_ms_per_step": ramp,
            "pcie_GBs": (pp.pp.h2d_bytes + d2h) / (e2e_ms / 1000.0) / 1e9,
            "registered_inputs": {"ms_per_step": reg_ms, "value": world * T * N / (reg_ms / 1000.0), "consistent": reg_ok,
