@@ -140,9 +140,12 @@ class ShardedVideoPostProcessor(object):
         pp.status.zero_()
         out = ops.nms_frames(d_boxes, d_scores, pp.seg_offsets, pp.nms_thresh, pp.N, want_mask=True,
                              status=pp.status, frame_major_out=True, out=(pp.d_idx, pp.d_cnt, pp.d_mask))
+        # the link waits for the exchange only, not for the NMS: on the side stream it fills the SMs the persistent
+        # NMS grid leaves idle in its last round
+        with torch.cuda.stream(self.side):
+            succ, link_iou = ops.link_frames(d_boxes, pp.seg_offsets, pp.N, halo, halo_row_base=pp.T * pp.N,
+                                             out=(pp.d_succ, pp.d_iou), halo_count=halo_count, ws=pp.slots[0].link_ws)
         main.wait_stream(self.side)
-        succ, link_iou = ops.link_frames(d_boxes, pp.seg_offsets, pp.N, halo, halo_row_base=pp.T * pp.N,
-                                         out=(pp.d_succ, pp.d_iou), halo_count=halo_count, ws=pp.slots[0].link_ws)
         res = pp._views(out)
         res.update(succ=succ, link_iou=link_iou)
         return res

@@ -186,6 +186,7 @@ class VideoPostProcessor(object):
         self.chunks = self._chunk_edges(self._uniform_off, T)
         self.s_in = torch.cuda.Stream(device=dev)
         self.s_out = torch.cuda.Stream(device=dev)
+        self.s_link = torch.cuda.Stream(device=dev)         # the link of the device-resident step runs beside the NMS
         self.slots = [_Slot(self, k % self.n_stage) for k in range(n_slots)]
         self._next_slot = 0
         self._graphs = {}
@@ -233,11 +234,18 @@ class VideoPostProcessor(object):
         return {"keep_idx": out[0].view(T, C, N), "keep_cnt": out[1], "keep_mask": out[2].view(T, C, N)}
 
     def _launch(self, d_boxes, d_scores, halo, halo_count=None):
+        """NMS and link of one device-resident shard.  The two kernels are independent: the link is forked onto a
+        side stream BEHIND the NMS launch, so its CTAs fill the SMs that the persistent NMS grid leaves idle in its
+        last, partially filled round (1000 frames over 592 CTA slots) instead of running after it."""
+        cur = torch.cuda.current_stream()
         self.status.zero_()
+        self.s_link.wait_stream(cur)
         out = ops.nms_frames(d_boxes, d_scores, self.seg_offsets, self.nms_thresh, self.N, want_mask=True,
                              status=self.status, frame_major_out=True, out=(self.d_idx, self.d_cnt, self.d_mask))
-        ops.link_frames(d_boxes, self.seg_offsets, self.N, halo, halo_row_base=self.T * self.N,
-                        out=(self.d_succ, self.d_iou), halo_count=halo_count, ws=self.slots[0].link_ws)
+        with torch.cuda.stream(self.s_link):
+            ops.link_frames(d_boxes, self.seg_offsets, self.N, halo, halo_row_base=self.T * self.N,
+                            out=(self.d_succ, self.d_iou), halo_count=halo_count, ws=self.slots[0].link_ws)
+        cur.wait_stream(self.s_link)
         return out
 
     def run_device(self, d_boxes, d_scores, halo=None, graph=False):
