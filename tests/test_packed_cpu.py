@@ -264,3 +264,18 @@ def test_greedy_tracker_input_from_packed_dets():
     opts = helpers.Opts(max_tracks=4, thres=0.6, nms_thres=None)
     tp, _ = oracle_np.greedily_track_from_raw_dets(g["vid"], pd.to_det_info(), helpers.fake_tracker, 3, opts)
     assert tp == g["out"]["greedy_raw"]
+
+
+def test_grouped_f32_groups_on_the_float32_frame_id():
+    """The kernels' view groups frames on the float32 cast of the frame id, like the [M,6] float32 matrix of
+    apply_vid_nms (vdet/video_det.py:53-56): ids that collide in float32 are one frame to vid_nms."""
+    big = 1 << 24
+    det = {"video": "v", "detections": [
+        {"frame": f, "bbox": [1, 2, 30, 40], "hash": "h", "scores": [{"class": "a", "class_index": 1, "score": 0.5}]}
+        for f in (3, big, big + 1, 3, big + 2)]}
+    pd = packed.PackedDets.from_det_proto(det)
+    off64, order64, seg64 = pd.frame_segments()
+    assert len(seg64) == 4                                           # exact ids: four frames
+    b, s, off, order, n = pd.grouped_f32()
+    assert off.tolist() == [0, 2, 4, 5] and n == 2                   # float32: 2^24 and 2^24 + 1 are one frame
+    assert order.tolist() == [0, 3, 1, 2, 4]

@@ -382,11 +382,15 @@ class PackedDets(object):
             for f, b, row in zip(self.frames.tolist(), self.boxes.tolist(), self.scores.tolist())]}
 
     # ---- tensor forms ----------------------------------------------------------------------
-    def frame_segments(self):
-        """Stable grouping by frame: ``(seg_offsets int64 [S+1], order int64 [M], seg_frames int64 [S])``;
-        ``order[seg_offsets[s]:seg_offsets[s+1]]`` are the source rows of frame ``seg_frames[s]``."""
-        order = np.argsort(self.frames, kind="stable")
-        seg_frames, counts = np.unique(self.frames, return_counts=True)
+    def frame_segments(self, as_f32=False):
+        """Stable grouping by frame: ``(seg_offsets int64 [S+1], order int64 [M], seg_frames [S])``;
+        ``order[seg_offsets[s]:seg_offsets[s+1]]`` are the source rows of frame ``seg_frames[s]``.
+        ``as_f32``: group on the float32 cast of the frame ids, as ``vid_nms`` sees them -- ``apply_vid_nms`` puts
+        the frame id into a float32 matrix (vdet/video_det.py:53-56), so ids that collide there (beyond 2^24) are
+        ONE frame to the suppression."""
+        keys = np.asarray(self.frames, dtype=np.float32) if as_f32 else self.frames
+        order = np.argsort(keys, kind="stable")
+        seg_frames, counts = np.unique(keys, return_counts=True)
         off = np.zeros(len(seg_frames) + 1, dtype=np.int64)
         np.cumsum(counts, out=off[1:])
         return off, order, seg_frames
@@ -395,7 +399,7 @@ class PackedDets(object):
         """Frame-grouped float32 arrays for the kernels: ``(boxes [M,4], scores [M,C], seg_offsets
         int32 [S+1], order int64 [M], max_seg_len)`` -- the cast ``apply_vid_nms`` performs on its
         ``[M,6]`` matrix (vdet/video_det.py:53-56)."""
-        off, order, _ = self.frame_segments()
+        off, order, _ = self.frame_segments(as_f32=True)
         if off[-1] >= (1 << 31):
             raise OverflowError("more than 2^31 detections")
         return (np.ascontiguousarray(self.boxes[order], dtype=np.float32),
