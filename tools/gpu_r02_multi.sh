@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round 2, multi-GPU call (gpurun --gpus N): host<->device ceiling of the box at 1/2/4/N ranks, multi-rank parity
 # tests, bench.py at every N (both arms at N=1 only: the reference arm does not change with N).
-#   gpurun --gpus 8 --timeout 1200 -- 'bash tools/gpu_r02_multi.sh 8'
+#   gpurun --gpus 8 --timeout 1200 -- 'bash tools/gpu_r02_multi.sh 8 [noprobe]'
 set -u
 NG=${1:-2}
 mkdir -p gpurun_out
@@ -17,14 +17,16 @@ run_n() {  # $1 ranks, rest: script + args
     python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $PORT "$@"; fi
 }
 el "h2d probe"
+[ "${2:-}" = "noprobe" ] && SKIP_PROBE=1 || SKIP_PROBE=0
 for n in 1 2 4 8; do
+  [ $SKIP_PROBE = 1 ] && continue
   [ $n -le $NG ] || continue
   timeout 120 bash -c "$(declare -f run_n); PORT=$((29700 + n)); run_n $n tools/h2d_scale_probe.py --reps 30" >> gpurun_out/h2d_probe_scale.json 2>> gpurun_out/multi.err
   if [ $n -ge 4 ]; then
     timeout 120 bash -c "$(declare -f run_n); PORT=$((29750 + n)); run_n $n tools/h2d_scale_probe.py --reps 30 --bind" >> gpurun_out/h2d_probe_scale.json 2>> gpurun_out/multi.err
   fi
 done
-python - <<'P'
+[ $SKIP_PROBE = 1 ] || python - <<'P'
 import json
 for line in open("gpurun_out/h2d_probe_scale.json"):
     try:
@@ -46,9 +48,11 @@ import json
 try:
     d = json.loads(open("gpurun_out/bench_n$n.json").read().strip().splitlines()[-1])
     e = d["e2e"]
-    print("N=$n value %.4g (%.3f ms)  e2e %.4g (%.3f ms, wall %.3f)  pinned %.3f ms  parity %s %s" % (
-        d["value"], d["ms_per_step"], e["value"], e["ms_per_step"], e["host_wall_ms_per_step"], e["pinned_resubmit"]["ms_per_step"],
-        d.get("parity"), d.get("parity_multi")))
+    c = e.get("box_ceiling", {})
+    print("N=$n value %.4g (%.4f ms)  e2e %.4g (%.3f ms)  ceiling stage+up %.3f up %.3f  registered %.3f  pinned %.3f ms  parity %s %s" % (
+        d["value"], d["ms_per_step"], e["value"], e["ms_per_step"], c.get("stage_plus_upload_ms", 0), c.get("upload_only_ms", 0),
+        e["registered_inputs"]["ms_per_step"], e["pinned_resubmit"]["ms_per_step"],
+        all(d["parity"][k] for k in ("e2e_equals_device_resident", "keep_lists_vs_oracle", "link_vs_oracle")), d.get("parity_multi")))
 except Exception as ex:
     print("bench N=$n unreadable:", ex)
 P
