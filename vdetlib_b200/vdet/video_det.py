@@ -25,8 +25,20 @@ def apply_vid_nms(det_proto, class_index, thres=0.3):
     logging.info('Apply NMS on video: {}'.format(det_proto['video']))
     new_det = {}
     new_det['video'] = det_proto['video']
-    boxes = np.asarray([[det['frame'], ] + list(det['bbox']) + [det_score(det, class_index), ]
-                        for det in det_proto['detections']], dtype='float32').reshape(-1, 6)
+    dets = det_proto['detections']
+
+    def score_of(det):
+        # det_score (utils/protocol.py:323-327) scans the det's score list for class_index; protos written by
+        # vdetlib list the classes in order, so the entry at position class_index - 1 is usually the one
+        sc = det['scores']
+        if 0 < class_index <= len(sc) and sc[class_index - 1]['class_index'] == class_index:
+            return sc[class_index - 1]['score']
+        return det_score(det, class_index)
+    boxes = np.empty((len(dets), 6), dtype='float32')              # the [M,6] float32 matrix of :53-56, column-wise
+    if len(dets):
+        boxes[:, 0] = [det['frame'] for det in dets]
+        boxes[:, 1:5] = [det['bbox'] for det in dets]
+        boxes[:, 5] = [score_of(det) for det in dets]
     keep = vid_nms(boxes, thresh=0.3)
     new_det['detections'] = copy.copy([det_proto['detections'][i] for i in keep])
     logging.info("{} / {} windows kept.".format(len(new_det['detections']), len(det_proto['detections'])))
