@@ -13,9 +13,13 @@ BASE_KEYS = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 
 def _latest_bench():
+    """The newest round's last committed 1-GPU line: rNN_bench_final.json, else the highest rNN_bench_vK.json."""
+    finals = sorted(glob.glob(os.path.join(ROOT, "profiles", "r[0-9]*_bench_final.json")))
     files = [f for f in glob.glob(os.path.join(ROOT, "profiles", "r[0-9]*_bench_v*.json"))]
-    assert files, "no committed bench line under profiles/"
+    assert files or finals, "no committed bench line under profiles/"
     files.sort(key=lambda f: (os.path.basename(f).split("_")[0], int(os.path.basename(f).split("_v")[1].split(".")[0])))
+    if finals and (not files or os.path.basename(finals[-1]).split("_")[0] >= os.path.basename(files[-1]).split("_")[0]):
+        return json.load(open(finals[-1])), finals[-1]
     return json.load(open(files[-1])), files[-1]
 
 
@@ -44,6 +48,18 @@ def test_committed_bench_line_has_the_contract_keys():
         assert k in e
     assert e["h2d_bytes_per_step"] == 1000 * 300 * (4 + 30) * 4 and e["d2h_bytes_per_step"] > 0
     assert e["value"] < line["value"]                                               # host buffers cannot beat resident inputs
+    # round 2: the end-to-end leg is the user's call (staging inside, ordered keep lists home), checked against the
+    # oracle after the loop, bounded by what the box delivers; the other BASELINE configs ride in the same line
+    assert "pageable" in e["input"] and "keep lists" in e["output"]
+    assert {"upload_only_ms", "stage_plus_upload_ms"} <= set(e["box_ceiling"])
+    assert e["registered_inputs"]["consistent"] is True and "pinned_resubmit" in e and "host_ms_per_step" in e
+    assert line["parity"] == {"e2e_equals_device_resident": True, "keep_lists_vs_oracle_frames": [0, 500, 999],
+                              "keep_lists_vs_oracle": True, "link_vs_oracle": True}
+    assert r["limiter"] == "issue" and "8(d)" in r["algorithmic_bytes_formula"] and "static" in r["traffic_source"]
+    assert {"config3_link", "config4_temporal", "config5_video"} <= set(line["configs"])
+    for cfg in line["configs"].values():
+        assert "cpu_baseline" in cfg and cfg["cpu_baseline"]["cores"] == 1
+    assert all(v["same"] for v in line["adapters"]["calls"].values())
     k = line["clocks"]
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(k)
     assert not set(k["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}

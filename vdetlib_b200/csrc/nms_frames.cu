@@ -127,7 +127,7 @@ extern "C" int vdet_nms_frames_f32(const float* boxes, int box_ld,
     const size_t base = nms_smem_bytes(nb, sort_blocks, 0, false);
     const size_t per_class = (size_t)(nb + 1) * sizeof(float);
     const size_t sm_smem = 228 * 1024, cta_reserved = 1024;
-    const int reg_limit = (nper > 16) ? 1 : 4;
+    const int reg_limit = (nper > 16) ? 1 : VDET_NMS_CTAS_PER_SM;
     auto fit = [&](size_t smem_cta) {                       // CTAs of that size per SM
         int k = (int)(sm_smem / (smem_cta + cta_reserved));
         return k > reg_limit ? reg_limit : k;
@@ -145,7 +145,7 @@ extern "C" int vdet_nms_frames_f32(const float* boxes, int box_ld,
             const int chunk_max = (int)((budget - base) / per_class);
             if (chunk_max < NMS_WARPS) continue;
             const int n_pass = (n_classes + chunk_max - 1) / chunk_max;
-            if (n_pass > 3) continue;
+            if (n_pass > (VDET_NMS_CTAS_PER_SM > 4 ? 4 : 3)) continue;
             int chunk = (n_classes + n_pass - 1) / n_pass;
             const int rounded = (chunk + NMS_WARPS - 1) / NMS_WARPS * NMS_WARPS;
             if (rounded <= chunk_max) chunk = rounded;

@@ -21,11 +21,17 @@
 #include "common.cuh"
 #include "warp_sort.cuh"
 
-// Build switch (tools/build_variant.py builds the other setting as a separate library for A/B timing):
+// Build switches (tools/build_variant.py builds the other setting as a separate library for A/B timing):
 //   VDET_TILE_PACKED   the 32x32 bit-matrix tile evaluates two columns per step on packed float32 pairs
 //                      (FADD2 / FMUL2); 0 = the scalar tile of round 1, kept for A/B timing.
 #ifndef VDET_TILE_PACKED
 #define VDET_TILE_PACKED 1
+#endif
+//   VDET_NMS_CTAS_PER_SM   resident CTAs per SM the register budget of the <= 512-key variants is compiled for
+//                      (4 = 64 registers per thread; 5 = 48 registers with ~350 bytes of spills per thread:
+//                      measured 0.375 ms against 0.325 on config 2)
+#ifndef VDET_NMS_CTAS_PER_SM
+#define VDET_NMS_CTAS_PER_SM 4
 #endif
 
 namespace vdet {
@@ -242,7 +248,7 @@ static __device__ __noinline__ void zero_division_check(const uint32_t* so, int 
 // network was the largest single item of the per-class work, the two extra probe chains cost a
 // third of what it saves.
 template <int NPER, int NPB, bool STAGE>
-__global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? 4 : 1)) nms_frames_kernel(const NmsFramesParams p) {
+__global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? VDET_NMS_CTAS_PER_SM : 1)) nms_frames_kernel(const NmsFramesParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NB = p.nb;
     const int W = NB >> 5;          // mask words per row (<= 32 in this variant)
