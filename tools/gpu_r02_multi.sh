@@ -52,7 +52,7 @@ try:
     print("N=$n value %.4g (%.4f ms)  e2e %.4g (%.3f ms)  ceiling stage+up %.3f up %.3f  registered %.3f  pinned %.3f ms  parity %s %s" % (
         d["value"], d["ms_per_step"], e["value"], e["ms_per_step"], c.get("stage_plus_upload_ms", 0), c.get("upload_only_ms", 0),
         e["registered_inputs"]["ms_per_step"], e["pinned_resubmit"]["ms_per_step"],
-        all(d["parity"][k] for k in ("e2e_equals_device_resident", "keep_lists_vs_oracle", "link_vs_oracle")), d.get("parity_multi")))
+        all(v for k, v in d["parity"].items() if isinstance(v, bool)), d.get("parity_multi")))
 except Exception as ex:
     print("bench N=$n unreadable:", ex)
 P
