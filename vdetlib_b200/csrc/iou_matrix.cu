@@ -18,17 +18,32 @@ namespace vdet {
 
 constexpr int IOU_THREADS = 256;
 constexpr int IOU_TILE_C = IOU_THREADS * 4;   // 1024 columns per CTA
-constexpr int IOU_TILE_R = 32;                // rows per CTA
+#ifndef VDET_IOU_STORE
+#define VDET_IOU_STORE 0          // 0: st.global.cs (evict first), 1: default policy, 2: st.global.wt
+#endif
+constexpr int IOU_TILE_R = 32;                // rows per CTA (float64 kernel; float32: 32 or 128, chosen per launch)
+constexpr int IOU_TILE_R_BIG = 128;           // float32, tall matrices: 16384^2 runs at 91.5 % of the measured HBM peak with
+                                              // 128-row tiles against 87.6 % with 32 (90.4 % with 64, 78.8 % with 16)
 
-template <bool VEC, bool FAST>
+__device__ __forceinline__ void iou_store4(float4* p, const float4 v) {
+#if VDET_IOU_STORE == 1
+    *p = v;
+#elif VDET_IOU_STORE == 2
+    __stwt(p, v);
+#else
+    __stcs(p, v);
+#endif
+}
+
+template <bool VEC, bool FAST, int TILE_R>
 __device__ __forceinline__ void iou_matrix_f32_body(const float4* __restrict__ a, int64_t na,
                                                                      const float4* __restrict__ b, int64_t nb,
                                                                      float* __restrict__ out) {
-    __shared__ float4 s_a[IOU_TILE_R];
-    __shared__ float s_aa[IOU_TILE_R];
+    __shared__ float4 s_a[TILE_R];
+    __shared__ float s_aa[TILE_R];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t c0 = (int64_t)blockIdx.x * IOU_TILE_C;
-    const int64_t r0 = (int64_t)blockIdx.y * IOU_TILE_R;
+    const int64_t r0 = (int64_t)blockIdx.y * TILE_R;
     // this thread's 4 columns (re-read here: cheap, L1-resident after the sanity pass)
     int64_t col[4];
     float4 bb[4];
@@ -42,14 +57,14 @@ __device__ __forceinline__ void iou_matrix_f32_body(const float4* __restrict__ a
         // inside the row loop -- seen as 8.3 instead of 6 FADD per IoU in the first ncu capture
         asm volatile("" : "+f"(ba[k]));
     }
-    if (tid < IOU_TILE_R) {
+    if (tid < TILE_R) {
         const int64_t r = r0 + tid;
         const float4 v = r < na ? __ldg(a + r) : make_float4(0.f, 0.f, 0.f, 0.f);
         s_a[tid] = v;
         s_aa[tid] = area_f32(v);
     }
     __syncthreads();
-    const int rows = (int)((na - r0) < IOU_TILE_R ? (na - r0) : IOU_TILE_R);
+    const int rows = (int)((na - r0) < TILE_R ? (na - r0) : TILE_R);
     // FAST (every box of the tile is sane): the four IoUs of a thread and row are two PACKED pairs -- FADD2 /
     // FMUL2 / FFMA2 evaluate both halves with one instruction each (common.cuh), ~14 instead of ~22
     // instructions per IoU, which is what moves this kernel from issue bound to HBM-write bound.
@@ -73,14 +88,14 @@ __device__ __forceinline__ void iou_matrix_f32_body(const float4* __restrict__ a
             }
         }
     };
-    if (VEC && rows == IOU_TILE_R && c0 + IOU_TILE_C <= nb) {
+    if (VEC && rows == TILE_R && c0 + IOU_TILE_C <= nb) {
         // interior tile: no bounds checks, one 16-byte streaming store per thread and row
         float* row = out + r0 * nb + c0 + 4 * tid;
 #pragma unroll 4
-        for (int r = 0; r < IOU_TILE_R; ++r, row += nb) {
+        for (int r = 0; r < TILE_R; ++r, row += nb) {
             float v[4];
             row_of_four(s_a[r], s_aa[r], v);
-            __stcs(reinterpret_cast<float4*>(row), make_float4(v[0], v[1], v[2], v[3]));
+            iou_store4(reinterpret_cast<float4*>(row), make_float4(v[0], v[1], v[2], v[3]));
         }
         return;
     }
@@ -107,22 +122,22 @@ __device__ __forceinline__ void iou_matrix_f32_body(const float4* __restrict__ a
 
 // The CTA first votes whether every box it touches is "sane" (common.cuh): if so the whole tile
 // uses the branch-free 6-instruction division, else the generic IEEE path.  Same bits either way.
-template <bool VEC>
+template <bool VEC, int TILE_R>
 __global__ void __launch_bounds__(IOU_THREADS) iou_matrix_f32_kernel(const float4* __restrict__ a, int64_t na,
                                                                      const float4* __restrict__ b, int64_t nb,
                                                                      float* __restrict__ out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t c0 = (int64_t)blockIdx.x * IOU_TILE_C;
-    const int64_t r0 = (int64_t)blockIdx.y * IOU_TILE_R;
+    const int64_t r0 = (int64_t)blockIdx.y * TILE_R;
     bool ok = true;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int64_t col = VEC ? (c0 + 4 * tid + k) : (c0 + warp * 128 + k * 32 + lane);
         if (col < nb) ok = ok && box_sane(__ldg(b + col));
     }
-    if (tid < IOU_TILE_R && r0 + tid < na) ok = ok && box_sane(__ldg(a + r0 + tid));
-    if (__syncthreads_and(ok)) iou_matrix_f32_body<VEC, true>(a, na, b, nb, out);
-    else iou_matrix_f32_body<VEC, false>(a, na, b, nb, out);
+    if (tid < TILE_R && r0 + tid < na) ok = ok && box_sane(__ldg(a + r0 + tid));
+    if (__syncthreads_and(ok)) iou_matrix_f32_body<VEC, true, TILE_R>(a, na, b, nb, out);
+    else iou_matrix_f32_body<VEC, false, TILE_R>(a, na, b, nb, out);
 }
 
 // utils/common.py:451-468 in float64, operation for operation.
@@ -220,15 +235,22 @@ extern "C" int vdet_iou_matrix_f32(const float* a, int64_t na, const float* b, i
     VDET_REQUIRE(na >= 0 && nb >= 0, "iou_matrix: negative size");
     if (na == 0 || nb == 0) return VDET_OK;
     VDET_REQUIRE(((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0, "iou_matrix: boxes must be 16-byte aligned");
-    const int64_t gx = (nb + IOU_TILE_C - 1) / IOU_TILE_C, gy = (na + IOU_TILE_R - 1) / IOU_TILE_R;
+    // tall matrices take 128-row tiles (fewer, longer CTAs: less per-CTA set-up per byte written); short ones keep
+    // 32 rows so that a few hundred rows still spread over the SMs
+    const int tile_r = na >= 2048 ? IOU_TILE_R_BIG : IOU_TILE_R;
+    const int64_t gx = (nb + IOU_TILE_C - 1) / IOU_TILE_C, gy = (na + tile_r - 1) / tile_r;
     dim3 grid((unsigned)gx, (unsigned)gy);
     VDET_REQUIRE(gy <= 65535, "iou_matrix: more than 2M rows per call");
     const bool vec = (nb % 4 == 0) && (((uintptr_t)out & 15) == 0);
     cudaStream_t st = (cudaStream_t)stream;
-    if (vec)
-        iou_matrix_f32_kernel<true><<<grid, IOU_THREADS, 0, st>>>((const float4*)a, na, (const float4*)b, nb, out);
-    else
-        iou_matrix_f32_kernel<false><<<grid, IOU_THREADS, 0, st>>>((const float4*)a, na, (const float4*)b, nb, out);
+    const float4 *a4 = (const float4*)a, *b4 = (const float4*)b;
+    if (tile_r == IOU_TILE_R_BIG) {
+        if (vec) iou_matrix_f32_kernel<true, IOU_TILE_R_BIG><<<grid, IOU_THREADS, 0, st>>>(a4, na, b4, nb, out);
+        else iou_matrix_f32_kernel<false, IOU_TILE_R_BIG><<<grid, IOU_THREADS, 0, st>>>(a4, na, b4, nb, out);
+    } else {
+        if (vec) iou_matrix_f32_kernel<true, IOU_TILE_R><<<grid, IOU_THREADS, 0, st>>>(a4, na, b4, nb, out);
+        else iou_matrix_f32_kernel<false, IOU_TILE_R><<<grid, IOU_THREADS, 0, st>>>(a4, na, b4, nb, out);
+    }
     VDET_LAUNCH_CHECK();
     return VDET_OK;
 }
