@@ -198,7 +198,8 @@ class VideoPostProcessor(object):
         self.chunks = self._chunk_edges(self._uniform_off, T)
         self.s_in = torch.cuda.Stream(device=dev)
         self.s_out = torch.cuda.Stream(device=dev)
-        self.s_link = torch.cuda.Stream(device=dev)         # the link of the device-resident step runs beside the NMS
+        self.s_link = torch.cuda.Stream(device=dev)         # the link of the device-resident step runs beside the NMS,
+        self.s_nms = torch.cuda.Stream(device=dev, priority=-1)    # which has the higher priority
         self.slots = [_Slot(self, k % self.n_stage) for k in range(n_slots)]
         self._next_slot = 0
         self._graphs = {}
@@ -251,12 +252,17 @@ class VideoPostProcessor(object):
         last, partially filled round (1000 frames over 592 CTA slots) instead of running after it."""
         cur = torch.cuda.current_stream()
         self.status.zero_()
+        self.s_nms.wait_stream(cur)
         self.s_link.wait_stream(cur)
-        out = ops.nms_frames(d_boxes, d_scores, self.seg_offsets, self.nms_thresh, self.N, want_mask=True,
-                             status=self.status, frame_major_out=True, out=(self.d_idx, self.d_cnt, self.d_mask))
+        # the NMS goes to a HIGH-priority stream and is launched first: whichever grid the hardware starts first, SM
+        # resources that become free go to NMS CTAs as long as any are pending, and the link takes what is left
+        with torch.cuda.stream(self.s_nms):
+            out = ops.nms_frames(d_boxes, d_scores, self.seg_offsets, self.nms_thresh, self.N, want_mask=True,
+                                 status=self.status, frame_major_out=True, out=(self.d_idx, self.d_cnt, self.d_mask))
         with torch.cuda.stream(self.s_link):
             ops.link_frames(d_boxes, self.seg_offsets, self.N, halo, halo_row_base=self.T * self.N,
                             out=(self.d_succ, self.d_iou), halo_count=halo_count, ws=self.slots[0].link_ws)
+        cur.wait_stream(self.s_nms)
         cur.wait_stream(self.s_link)
         return out
 
