@@ -631,7 +631,8 @@ def run_b200(args):
                                    "ranks); ratios near 1 = the step runs at what the host side of the box delivers"
                                    % pp.pp.h2d_bytes},
            "pinned_resubmit": {"ms_per_step": pinned_ms, "value": world * T * N / (pinned_ms / 1000.0),
-                               "note": "round-1 definition: the same pre-pinned shard re-uploaded every step (no staging copy)"},
+                               "note": "round-1 definition: the same pre-pinned shard re-uploaded every step (no staging copy) -- what a "
+                                       "producer that writes into input_buffers() and calls commit_inputs() / submit_staged() gets"},
            "api": "vdetlib_b200.dist.ShardedVideoPostProcessor.submit_host(boxes, scores) / collect(ticket)"}
 
     # ---- parity, after the timed regions (the oracle only checks; it is never timed or shipped) -------------

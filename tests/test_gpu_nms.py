@@ -415,6 +415,49 @@ def test_video_postprocessor_registered_caller_arrays():
         pp.register_host_arrays(shards[0][0].astype(np.float64))
 
 
+def test_video_postprocessor_producer_writes_in_place(graph=True):
+    """input_buffers / commit_inputs: the producer fills the pinned upload buffers itself (no staging copy); uniform
+    and ragged shards, two steps in flight, each slot handing out its own buffers."""
+    from vdetlib_b200.vdet.video_det import VideoPostProcessor
+    T, N, C = 6, 200, 5
+    pp = VideoPostProcessor(T, N, C, 0.3, n_chunks=3)
+    shards = [synth.boxes_scores(T, N, C, seed=990 + k) for k in range(3)]
+    tickets = []
+    for k in range(2):
+        hb, hs = pp.input_buffers()
+        assert hb.shape == (T * N, 4) and hs.shape == (T * N, C)
+        hb[:] = shards[k][0].reshape(-1, 4)
+        hs[:] = shards[k][1].reshape(-1, C)
+        pp.commit_inputs()
+        tickets.append(pp.submit_staged(graph=(graph and k == 1)))
+    with pytest.raises(RuntimeError):
+        pp.input_buffers()                                   # both slots in flight: no buffer is the caller's
+    for k in range(2):
+        out = pp.collect(tickets[k])
+        km, ki, kc = c_oracle.nms_frames(*shards[k], 0.3)
+        assert np.array_equal(out["keep_cnt"], kc) and np.array_equal(out.keep_mask(), km)
+        ls, lb = c_oracle.link_f32(shards[k][0])
+        assert np.array_equal(out["succ"][:(T - 1) * N].reshape(T - 1, N) - np.arange(1, T)[:, None] * N, ls)
+    # ragged, in place: packed rows from row 0
+    counts = np.asarray([200, 0, 31, 7], np.int32)
+    b, s = shards[2]
+    hb, hs = pp.input_buffers()
+    r = 0
+    for t, n in enumerate(counts):
+        hb[r:r + n] = b[t, :n]
+        hs[r:r + n] = s[t, :n]
+        r += n
+    pp.commit_inputs(counts)
+    out = pp.collect(pp.submit_staged())
+    km, ki, kc = c_oracle.nms_frames(b[:4], s[:4], 0.3, counts)
+    assert np.array_equal(out["keep_cnt"], kc)
+    for t in range(4):
+        for c in range(C):
+            assert np.array_equal(out.keep_list(t, c), ki[t, c, :kc[t, c]]), (t, c)
+    with pytest.raises(ValueError):
+        pp.commit_inputs([N + 1])
+
+
 def test_video_postprocessor_ragged_frames():
     """Ragged shards (packed rows + counts) through the staged pipeline, chunk edges balanced by rows."""
     from vdetlib_b200.vdet.video_det import VideoPostProcessor

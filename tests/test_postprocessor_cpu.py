@@ -165,3 +165,4 @@ def test_gpu_test_bodies_of_the_streaming_and_ragged_paths_on_the_harness(fake):
     import test_gpu_nms
     test_gpu_nms.test_video_postprocessor_streams_new_shards_from_pageable_memory(False)
     test_gpu_nms.test_video_postprocessor_ragged_frames()
+    test_gpu_nms.test_video_postprocessor_producer_writes_in_place(False)

@@ -165,9 +165,18 @@ class ShardedVideoPostProcessor(object):
         return self.pp.submit_host(boxes, scores, counts, halo_fn=self._halo_fn if multi else None, graph=graph)
 
     def submit_staged(self, graph=True):
-        """The same from inputs already staged with ``self.pp.stage(...)`` (re-submission of one shard)."""
+        """The same from inputs already staged with ``self.pp.stage(...)`` (re-submission of one shard) or written in
+        place (``input_buffers`` / ``commit_inputs``)."""
         multi = self.exchange.world > 1
         return self.pp.submit_staged(halo_fn=self._halo_fn if multi else None, graph=graph)
+
+    def input_buffers(self):
+        """The pinned upload buffers of the next step, for a producer that writes in place
+        (VideoPostProcessor.input_buffers); follow with :meth:`commit_inputs` and :meth:`submit_staged`."""
+        return self.pp.input_buffers()
+
+    def commit_inputs(self, counts=None):
+        self.pp.commit_inputs(counts)
 
     def step_host(self, boxes=None, scores=None, counts=None, graph=False):
         """The end-to-end step, synchronous (host arrays, or the staged shard when none are given)."""

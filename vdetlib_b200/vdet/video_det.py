@@ -338,28 +338,11 @@ class VideoPostProcessor(object):
         CPU caches and the copy engine then reads them at roughly half the PCIe rate (profiles/r01_pcie.md).
         With one staging set (``n_stage=1``) every step in flight reads these buffers: collect all outstanding
         steps before restaging.  With a set per slot only the slot about to be reused must have been collected."""
-        target = self._target_slot()
-        if any(sl.busy and sl.stage_set == target.stage_set for sl in self.slots):
-            raise RuntimeError("stage: a submitted step still reads the staging buffers; collect() it first")
+        target = self._free_target("stage")
         b = np.ascontiguousarray(boxes, dtype=np.float32).reshape(-1, 4)
         s = np.ascontiguousarray(scores, dtype=np.float32).reshape(-1, self.C)
-        if counts is None:
-            n_frames, rows, uniform = self.T, self.T * self.N, True
-            if b.shape[0] != rows or s.shape[0] != rows:
-                raise ValueError("stage: expected %d rows" % rows)
-            if self._staged[target.stage_set] is not None and not self._staged[target.stage_set][2]:
-                target.h_seg.numpy()[:] = self._uniform_off
-        else:
-            cnt = np.asarray(counts, dtype=np.int64).reshape(-1)
-            n_frames, rows, uniform = int(cnt.shape[0]), int(cnt.sum()), False
-            if n_frames < 1 or n_frames > self.T or (cnt < 0).any() or int(cnt.max()) > self.N:
-                raise ValueError("stage: counts must describe 1..%d frames of 0..%d boxes" % (self.T, self.N))
-            if b.shape[0] != rows or s.shape[0] != rows:
-                raise ValueError("stage: counts add up to %d rows, got %d / %d" % (rows, b.shape[0], s.shape[0]))
-            seg = target.h_seg.numpy()
-            seg[0] = 0
-            np.cumsum(cnt, out=seg[1:n_frames + 1])
-            seg[n_frames + 1:] = rows
+        shape = self._describe(target, counts, b.shape[0], s.shape[0])
+        n_frames, rows, uniform = shape
         rb, rs = self._registered.get(b.ctypes.data), self._registered.get(s.ctypes.data)
         if rb is not None and rs is not None and rb[0].nbytes >= b.nbytes and rs[0].nbytes >= s.nbytes:
             # the caller's own arrays, pinned in place: the step uploads from them directly
@@ -369,7 +352,53 @@ class VideoPostProcessor(object):
                 ops.host_copy_stream(target.h_boxes[:rows], b, self.stage_threads)
                 ops.host_copy_stream(target.h_scores[:rows], s, self.stage_threads)
             self._src[target.stage_set] = (target.h_boxes, target.h_scores)
-        self._staged[target.stage_set] = (n_frames, rows, uniform)
+        self._staged[target.stage_set] = shape
+
+    def _free_target(self, who):
+        target = self._target_slot()
+        if any(sl.busy and sl.stage_set == target.stage_set for sl in self.slots):
+            raise RuntimeError("%s: a submitted step still reads the staging buffers; collect() it first" % who)
+        return target
+
+    def _describe(self, target, counts, box_rows, score_rows):
+        """Validate the shard's shape and write its segment table; returns (n_frames, rows, uniform)."""
+        if counts is None:
+            n_frames, rows, uniform = self.T, self.T * self.N, True
+            if box_rows != rows or score_rows != rows:
+                raise ValueError("stage: expected %d rows" % rows)
+            if self._staged[target.stage_set] is not None and not self._staged[target.stage_set][2]:
+                target.h_seg.numpy()[:] = self._uniform_off
+        else:
+            cnt = np.asarray(counts, dtype=np.int64).reshape(-1)
+            n_frames, rows, uniform = int(cnt.shape[0]), int(cnt.sum()), False
+            if n_frames < 1 or n_frames > self.T or (cnt < 0).any() or int(cnt.max()) > self.N:
+                raise ValueError("stage: counts must describe 1..%d frames of 0..%d boxes" % (self.T, self.N))
+            if box_rows != rows or score_rows != rows:
+                raise ValueError("stage: counts add up to %d rows, got %d / %d" % (rows, box_rows, score_rows))
+            seg = target.h_seg.numpy()
+            seg[0] = 0
+            np.cumsum(cnt, out=seg[1:n_frames + 1])
+            seg[n_frames + 1:] = rows
+        return n_frames, rows, uniform
+
+    def input_buffers(self):
+        """Producer-side zero copy: NumPy views ``(boxes [T*N, 4], scores [T*N, C])`` of the pinned upload buffers
+        of the NEXT step to be submitted.  A producer that writes its detections straight into them (packed rows
+        from row 0; the rest is ignored) and then calls :meth:`commit_inputs` skips the staging copy altogether --
+        one pass over host memory (the DMA read) instead of three.  The views stay valid for the life of the
+        processor; they belong to the caller until ``commit_inputs`` + ``submit_staged`` and again after the
+        ``collect`` of that step."""
+        target = self._free_target("input_buffers")
+        return target.h_boxes.numpy(), target.h_scores.numpy()
+
+    def commit_inputs(self, counts=None):
+        """Declare the buffers handed out by :meth:`input_buffers` filled: a full uniform shard, or ``counts[t]``
+        boxes per frame in packed rows.  Follow with :meth:`submit_staged`."""
+        target = self._free_target("commit_inputs")
+        rows = self.T * self.N if counts is None else int(np.asarray(counts, dtype=np.int64).sum())
+        shape = self._describe(target, counts, rows, rows)
+        self._src[target.stage_set] = (target.h_boxes, target.h_scores)
+        self._staged[target.stage_set] = shape
 
     # ---- one step on the streams -----------------------------------------------------------
     def _enqueue(self, sl, shape, halo, halo_count, fork):
