@@ -10,6 +10,7 @@
 #include <condition_variable>
 #include <cstring>
 #include <mutex>
+#include <cstdlib>
 #include <thread>
 #include <vector>
 #include <unistd.h>
@@ -206,8 +207,12 @@ int vdet_host_copy_stream_mt(void* dst, const void* src, size_t bytes, int n_thr
         return VDET_ERR_INVALID;
     }
     if (n_threads <= 0) {                                   // auto: one core moves ~10 GB/s, the DRAM bus several times that
+        static const int env_threads = [] {                 // VDET_STAGE_THREADS: the auto value, fixed by the operator
+            const char* e = std::getenv("VDET_STAGE_THREADS");
+            return e ? std::atoi(e) : 0;
+        }();
         const unsigned hw = std::thread::hardware_concurrency() / 2;     // physical cores, roughly
-        n_threads = (int)(hw == 0 ? 1 : (hw > 8 ? 8 : hw));
+        n_threads = env_threads > 0 ? env_threads : (int)(hw == 0 ? 1 : (hw > 8 ? 8 : hw));
         if (bytes < (size_t)(4u << 20)) n_threads = 1;      // not worth waking the pool
     }
     if (n_threads > 64) n_threads = 64;
