@@ -72,9 +72,11 @@ def _link_oracle_packed(b, counts):
     return np.concatenate(ws) if ws else np.zeros(0, np.int64), np.concatenate(wb) if wb else np.zeros(0, np.float32), off
 
 
-@pytest.mark.parametrize("T,N", [(2, 1), (5, 63), (4, 300), (3, 1000), (3, 1500)])
-def test_link_vs_oracle(T, N):
-    b, _ = synth.boxes_scores(T, N, 1, seed=T + N)
+@pytest.mark.parametrize("T,N,integer", [(2, 1, False), (5, 63, False), (4, 300, False), (3, 1000, False), (3, 1500, False),
+                                         (5, 300, True), (3, 700, True)])
+def test_link_vs_oracle(T, N, integer):
+    # integer coordinates: IoUs are ratios of small integers, so equal maxima occur (the FIRST arg-max wins)
+    b, _ = synth.boxes_scores(T, N, 1, seed=T + N, integer=integer)
     counts = np.full(T, N, np.int32)
     want_s, want_b, off = _link_oracle_packed(b, counts)
     db = torch.from_numpy(b.reshape(-1, 4)).to(DEV)

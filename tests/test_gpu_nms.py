@@ -146,6 +146,52 @@ def test_nms_frames_vs_oracle(T, N, C, thr):
     assert torch.equal(keep_idx2, keep_idx) and torch.equal(keep_cnt2.cpu(), torch.from_numpy(keep_cnt))
 
 
+@pytest.mark.parametrize("T,N,C,thr", [(6, 300, 5, 0.5), (6, 300, 5, 0.3), (6, 300, 5, 0.25), (5, 96, 3, 1.0 / 3.0),
+                                      (3, 1200, 2, 0.5), (2, 2048, 2, 0.25), (4, 300, 4, 0.2)])
+def test_nms_frames_integer_boxes_hit_the_threshold_exactly(T, N, C, thr):
+    """SURVEY 8(d)'s "integer" variant: rounded coordinates make IoU a ratio of small integers, so IoU == thresh
+    (>= suppresses, nms.pyx:64) and IoUs whose float32 quotient straddles the double threshold really occur -- the
+    pairs the division-free filter must hand to the exact division.  Every frame also gets exact duplicates."""
+    b, s = synth.boxes_scores(T, N, C, seed=77 * T + N, integer=True)
+    b[:, 1::7] = b[:, 0::7][:, :b[:, 1::7].shape[1]]            # duplicates: IoU exactly 1
+    # construct pairs with IoU exactly 1/2, 1/3, 1/4 and 3/10: [0,0,w-1,h-1] against a box of the same height
+    b[:, 2] = (10, 10, 29, 19)                                  # 20 x 10 = 200
+    b[:, 3] = (10, 10, 19, 19)                                  # inside it, 100: IoU 1/2
+    b[:, 4] = (400, 10, 429, 19)                                # 300
+    b[:, 5] = (400, 10, 409, 19)                                # 100 inside 300: IoU 1/3
+    b[:, 6] = (700, 10, 739, 19)                                # 400
+    b[:, 8] = (700, 10, 709, 19)                                # IoU 1/4
+    b[:, 9] = (900, 300, 999, 309)                              # 1000
+    b[:, 10] = (900, 300, 929, 309)                             # 300 inside 1000: IoU 3/10
+    b[:, 11] = (900, 500, 949, 509)                             # 500
+    b[:, 12] = (900, 500, 909, 509)                             # IoU 1/5
+    km, ki, kc = c_oracle.nms_frames(b, s, thr)
+    dev = torch.device("cuda")
+    seg = ops.seg_offsets_uniform(T, N, dev)
+    keep_idx, keep_cnt, keep_mask, status = ops.nms_frames(torch.from_numpy(b.reshape(-1, 4)).to(dev),
+                                                           torch.from_numpy(s.reshape(-1, C)).to(dev), seg, thr, N,
+                                                           want_mask=True, frame_major_out=True)
+    assert ops.raise_for_status(status) == 0
+    assert np.array_equal(keep_cnt.cpu().numpy(), kc)
+    assert np.array_equal(keep_mask.cpu().numpy().reshape(T, C, N), km)
+    gi = keep_idx.cpu().numpy().reshape(T, C, N)
+    want = np.where(ki >= 0, ki + (np.arange(T) * N)[:, None, None], -1)
+    assert np.array_equal(gi, want)
+    # the constructed pair that sits exactly on this threshold is suppressed by its partner whenever the partner
+    # ranks higher (>=, not >): check it through the oracle's own mask so the test cannot pass vacuously
+    on_thr = {0.5: (2, 3), 0.25: (6, 8), 0.2: (11, 12)}.get(thr)
+    if on_thr:
+        i, j = on_thr
+        hit = 0
+        for t in range(T):
+            for c in range(C):
+                hi, lo = (i, j) if s[t, i, c] > s[t, j, c] else (j, i)
+                if km[t, c, hi]:
+                    assert not km[t, c, lo]
+                    hit += 1
+        assert hit > 0
+
+
 def test_nms_frames_ragged():
     rng = np.random.default_rng(5)
     counts = np.asarray([0, 1, 40, 0, 300, 33, 64, 2], np.int32)
