@@ -12,8 +12,14 @@ static void plan_items(NmsFramesParams& p, int slots) {
     // Only launches that cannot fill the grid once are split (a single image with 30 classes, a short
     // clip): measured on config 2, splitting the LAST round of a multi-round launch does not pay --
     // the CTAs of a thin last round already run alone on their SMs and finish early.
-    if (p.n_segs * 2 > slots) return;
-    const int rem = p.n_segs;
+    int rem = p.n_segs;
+    if (p.n_segs * 2 > slots) {
+        // measurement hook: cut the frames of a thin LAST round (at most half the slots) into class ranges
+        const char* e = getenv("VDET_NMS_SPLIT_TAIL");
+        if (!(e && atoi(e))) return;
+        rem = p.n_segs % slots;
+        if (rem == 0 || rem * 2 > slots) return;
+    }
     int ns = slots / rem;
     if (ns > p.n_classes) ns = p.n_classes;
     if (ns > 8) ns = 8;
@@ -23,17 +29,19 @@ static void plan_items(NmsFramesParams& p, int slots) {
     p.n_items = p.split_from + rem * ns;
 }
 
-static size_t nms_smem_bytes(int nb, int sort_blocks, int n_classes, bool stage) {
+static size_t nms_smem_bytes(int nb, int sort_blocks, int n_classes, bool stage, int warps) {
     const int W = nb / 32, WS = W | 1;
     size_t b = (size_t)nb * (sizeof(float4) + sizeof(float) + sizeof(int32_t));
     b += (size_t)nb * WS * sizeof(uint32_t);
-    b += (size_t)NMS_WARPS * sort_blocks * 33 * sizeof(uint32_t);      // per-warp key / order scratch, skewed 32-key blocks
+    b += (size_t)warps * sort_blocks * 33 * sizeof(uint32_t);      // per-warp key / order scratch, skewed 32-key blocks
     if (stage) b += (size_t)n_classes * (nb + 1) * sizeof(float);
     return b;
 }
 
 template <int NPER>
-static int launch_nms_frames(const NmsFramesParams& p, size_t smem, int grid, cudaStream_t st) {
+static int launch_nms_frames(int threads, const NmsFramesParams& p, size_t smem, int grid, cudaStream_t st) {
+    if (NPER <= 8 && threads == NMS_THREADS_WIDE)          // staged only (see the plan in vdet_nms_frames_f32)
+        return launch_nms_frames_t<(NPER <= 8 ? NPER : 8), 0, true, NMS_THREADS_WIDE>(p, smem, grid, st);
     return p.stage ? launch_nms_frames_t<NPER, 0, true>(p, smem, grid, st)
                    : launch_nms_frames_t<NPER, 0, false>(p, smem, grid, st);
 }
@@ -124,50 +132,72 @@ extern "C" int vdet_nms_frames_f32(const float* boxes, int box_ld,
     // shared memory decides the rest.  When staging every class at once would cost a CTA slot, the
     // classes are staged in up to 3 chunks (multiples of the warp count) instead.
     const bool want_stage = (score_ldr != 1);
-    const size_t base = nms_smem_bytes(nb, sort_blocks, 0, false);
     const size_t per_class = (size_t)(nb + 1) * sizeof(float);
     const size_t sm_smem = 228 * 1024, cta_reserved = 1024;
-    const int reg_limit = (nper > 16) ? 1 : VDET_NMS_CTAS_PER_SM;
-    auto fit = [&](size_t smem_cta) {                       // CTAs of that size per SM
-        int k = (int)(sm_smem / (smem_cta + cta_reserved));
-        return k > reg_limit ? reg_limit : k;
-    };
-    p.stage = (want_stage && base + n_classes * per_class <= 100 * 1024) ? 1 : 0;
-    p.cls_chunk = n_classes;
-    int per_sm = fit(base + (p.stage ? n_classes * per_class : 0));
     int forced = 0;
     if (const char* e = getenv("VDET_NMS_PER_SM")) forced = atoi(e);      // measurement hook
-    if (p.stage && n_classes > NMS_WARPS) {
-        for (int want = reg_limit; want > per_sm; --want) {
-            if (forced > 0 && want > forced) continue;
-            const size_t budget = sm_smem / want - cta_reserved;
-            if (budget <= base) continue;
-            const int chunk_max = (int)((budget - base) / per_class);
-            if (chunk_max < NMS_WARPS) continue;
-            const int n_pass = (n_classes + chunk_max - 1) / chunk_max;
-            if (n_pass > (VDET_NMS_CTAS_PER_SM > 4 ? 4 : 3)) continue;
-            int chunk = (n_classes + n_pass - 1) / n_pass;
-            const int rounded = (chunk + NMS_WARPS - 1) / NMS_WARPS * NMS_WARPS;
-            if (rounded <= chunk_max) chunk = rounded;
-            p.cls_chunk = chunk;
-            per_sm = want;
-            break;
+    struct Plan { int stage, cls_chunk, per_sm; size_t smem; };
+    auto plan_for = [&](const int warps, const int reg_limit) {
+        Plan q;
+        const size_t base = nms_smem_bytes(nb, sort_blocks, 0, false, warps);
+        auto fit = [&](size_t smem_cta) {                   // CTAs of that size per SM
+            int k = (int)(sm_smem / (smem_cta + cta_reserved));
+            return k > reg_limit ? reg_limit : k;
+        };
+        q.stage = (want_stage && base + n_classes * per_class <= 100 * 1024) ? 1 : 0;
+        q.cls_chunk = n_classes;
+        q.per_sm = fit(base + (q.stage ? n_classes * per_class : 0));
+        if (q.stage && n_classes > warps) {
+            for (int want = reg_limit; want > q.per_sm; --want) {
+                if (forced > 0 && want > forced) continue;
+                const size_t budget = sm_smem / want - cta_reserved;
+                if (budget <= base) continue;
+                const int chunk_max = (int)((budget - base) / per_class);
+                if (chunk_max < warps) continue;
+                const int n_pass = (n_classes + chunk_max - 1) / chunk_max;
+                if (n_pass > (VDET_NMS_CTAS_PER_SM > 4 ? 4 : 3)) continue;
+                int chunk = (n_classes + n_pass - 1) / n_pass;
+                const int rounded = (chunk + warps - 1) / warps * warps;
+                if (rounded <= chunk_max) chunk = rounded;
+                q.cls_chunk = chunk;
+                q.per_sm = want;
+                break;
+            }
         }
+        if (forced > 0 && q.per_sm > forced) q.per_sm = forced;
+        if (q.per_sm < 1) q.per_sm = 1;
+        q.smem = base + (q.stage ? (size_t)(q.cls_chunk < n_classes ? q.cls_chunk : n_classes) * per_class : 0);
+        return q;
+    };
+    // CTA shape.  Default: 8 warps, up to 4 CTAs per SM, classes staged in up to 3 chunks.  Wide: 10 warps, 3 CTAs per
+    // SM -- taken when every class of the frame is staged at once at that residency (no chunk barriers) and there
+    // are enough classes to occupy the warps; frames of at most 320 boxes only (the kernels built for it).
+    int threads = NMS_THREADS;
+    Plan plan = plan_for(NMS_THREADS / 32, (nper > 16) ? 1 : VDET_NMS_CTAS_PER_SM);
+    if (nper <= 8 && want_stage) {
+        const Plan wide = plan_for(NMS_THREADS_WIDE / 32, NMS_CTAS_WIDE);
+        bool take = wide.stage && wide.cls_chunk >= n_classes && wide.per_sm == NMS_CTAS_WIDE && n_classes >= NMS_THREADS_WIDE / 32;
+        if (const char* e = getenv("VDET_NMS_THREADS")) {                 // measurement hook: 256 / 320
+            const int t = atoi(e);
+            if (t == NMS_THREADS) take = false;
+            if (t == NMS_THREADS_WIDE) take = wide.stage != 0;
+        }
+        if (take) { threads = NMS_THREADS_WIDE; plan = wide; }
     }
-    if (forced > 0 && per_sm > forced) per_sm = forced;
-    if (per_sm < 1) per_sm = 1;
-    const size_t smem = base + (p.stage ? (size_t)(p.cls_chunk < n_classes ? p.cls_chunk : n_classes) * per_class : 0);
-    int grid = usable_sm_count() * per_sm;
+    p.stage = plan.stage;
+    p.cls_chunk = plan.cls_chunk;
+    const size_t smem = plan.smem;
+    int grid = usable_sm_count() * plan.per_sm;
     plan_items(p, grid);
     if (grid > p.n_items) grid = p.n_items;
     cudaStream_t st = (cudaStream_t)stream;
-    if (npb) return launch_nms_frames_split(nper, npb, p, smem, grid, st);
+    if (npb) return launch_nms_frames_split(nper, npb, threads, p, smem, grid, st);
     switch (nper) {
-        case 1:  return launch_nms_frames<1>(p, smem, grid, st);
-        case 2:  return launch_nms_frames<2>(p, smem, grid, st);
-        case 4:  return launch_nms_frames<4>(p, smem, grid, st);
-        case 8:  return launch_nms_frames<8>(p, smem, grid, st);
-        case 16: return launch_nms_frames<16>(p, smem, grid, st);
-        default: return launch_nms_frames<32>(p, smem, grid, st);
+        case 1:  return launch_nms_frames<1>(threads, p, smem, grid, st);
+        case 2:  return launch_nms_frames<2>(threads, p, smem, grid, st);
+        case 4:  return launch_nms_frames<4>(threads, p, smem, grid, st);
+        case 8:  return launch_nms_frames<8>(threads, p, smem, grid, st);
+        case 16: return launch_nms_frames<16>(threads, p, smem, grid, st);
+        default: return launch_nms_frames<32>(threads, p, smem, grid, st);
     }
 }

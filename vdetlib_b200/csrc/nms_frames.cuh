@@ -86,8 +86,12 @@ __device__ __forceinline__ void lb_search(const uint32_t base_b, const uint32_t 
 __device__ __forceinline__ uint32_t unskew(const uint32_t words) { return words - words / 33u; }
 
 
+// CTA shapes of the <= 1024-box variants: 8 warps, four CTAs per SM (64 registers per thread), or -- for frames of at
+// most 320 boxes whose classes are all staged at once -- 10 warps, three CTAs per SM: 30 classes are three per warp
+// with no chunk barrier in between (config 2: 0.294 -> 0.277 ms, profiles/r02_nms_variants.md).
 constexpr int NMS_THREADS = 256;
-constexpr int NMS_WARPS = NMS_THREADS / 32;
+constexpr int NMS_THREADS_WIDE = 320;
+constexpr int NMS_CTAS_WIDE = 3;
 
 struct NmsFramesParams {
     const float* boxes; int box_ld; int box_vec;
@@ -247,8 +251,11 @@ static __device__ __noinline__ void zero_division_check(const uint32_t* so, int 
 // sorts 256 + 64 keys (330 compare-exchanges per lane) instead of padding to a 512-key network (720): the
 // network was the largest single item of the per-class work, the two extra probe chains cost a
 // third of what it saves.
-template <int NPER, int NPB, bool STAGE>
-__global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? VDET_NMS_CTAS_PER_SM : 1)) nms_frames_kernel(const NmsFramesParams p) {
+template <int NPER, int NPB, bool STAGE, int THREADS = NMS_THREADS>
+__global__ void __launch_bounds__(THREADS, (NPER <= 16 ? (THREADS > NMS_THREADS ? NMS_CTAS_WIDE : VDET_NMS_CTAS_PER_SM) : 1))
+nms_frames_kernel(const NmsFramesParams p) {
+    constexpr int NMS_THREADS = THREADS;                 // (shadows the default CTA shape)
+    constexpr int NMS_WARPS = THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NB = p.nb;
     const int W = NB >> 5;          // mask words per row (<= 32 in this variant)
@@ -261,6 +268,7 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? VDET_NMS_CTAS_PER_S
     uint32_t* sord = smask + (size_t)NB * WS;                       // [NMS_WARPS][so_words] order scratch
     uint32_t* sscore = sord + NMS_WARPS * p.so_words;             // staged scores, already as sort keys
     __shared__ int s_zero_union;
+    __shared__ int s_next_class;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -285,6 +293,7 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? VDET_NMS_CTAS_PER_S
         }
         // ---- A: stage boxes, areas, original row ids (and scores) ------------------------
         if (tid == 0) s_zero_union = 0;
+        if (tid == 0) s_next_class = c_begin;
         bool all_sane = true;
         for (int e = tid; e < NB; e += NMS_THREADS) {
             float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -330,7 +339,7 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? VDET_NMS_CTAS_PER_S
             int t = 0;
             for (int rb = 0; rb < Wn; ++rb) {
                 for (int cb = rb; cb < Wn; ++cb, ++t) {
-                    if ((t & (NMS_WARPS - 1)) != warp) continue;
+                    if ((NMS_WARPS & (NMS_WARPS - 1)) == 0 ? ((t & (NMS_WARPS - 1)) != warp) : (t % NMS_WARPS != warp)) continue;
                     const int i = rb * 32 + lane;
                     const float4 bi = sbox[i];
                     const float ai = sarea[i];
@@ -363,9 +372,17 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? VDET_NMS_CTAS_PER_S
         if (STAGE && c0 != c_begin) {
             __syncthreads();                              // every warp is done with the previous chunk's keys
             stage_scores(c0, c1);
+            if (tid == 0) s_next_class = c0;
             __syncthreads();
         }
-        for (int c = c0 + warp; c < c1; c += NMS_WARPS) {
+        // the warps take the classes of the chunk from a shared counter: the cost of a class follows its keep count
+        // (one trip of the walk per kept box), and a round-robin deal leaves the CTA waiting for its unluckiest
+        // warp at every chunk barrier (config 2: 0.325 -> 0.294 ms)
+        for (;;) {
+            int c = 0;
+            if (lane == 0) c = atomicAdd(&s_next_class, 1);
+            c = __shfl_sync(FULL, c, 0);
+            if (c >= c1) break;
             const uint32_t* sc_smem = sscore + (c - c0) * SST;
             const float* sc_glob = p.scores + (int64_t)c * p.score_ldc;
             auto score_key = [&](const int e) -> uint32_t {
@@ -618,20 +635,20 @@ __global__ void __launch_bounds__(NMS_THREADS, (NPER <= 16 ? VDET_NMS_CTAS_PER_S
     }
 }
 
-template <int NPER, int NPB, bool STAGE>
+template <int NPER, int NPB, bool STAGE, int THREADS = NMS_THREADS>
 static int launch_nms_frames_t(const NmsFramesParams& p, size_t smem, int grid, cudaStream_t st) {
-    if (smem > max_dynamic_smem(nms_frames_kernel<NPER, NPB, STAGE>)) {
+    if (smem > max_dynamic_smem(nms_frames_kernel<NPER, NPB, STAGE, THREADS>)) {
         set_error("nms_frames: %zu bytes of shared memory needed", smem);
         return VDET_ERR_UNSUPPORTED;
     }
-    VDET_CUDA(allow_dynamic_smem(nms_frames_kernel<NPER, NPB, STAGE>, smem));
-    nms_frames_kernel<NPER, NPB, STAGE><<<grid, NMS_THREADS, smem, st>>>(p);
+    VDET_CUDA(allow_dynamic_smem(nms_frames_kernel<NPER, NPB, STAGE, THREADS>, smem));
+    nms_frames_kernel<NPER, NPB, STAGE, THREADS><<<grid, THREADS, smem, st>>>(p);
     VDET_LAUNCH_CHECK();
     return VDET_OK;
 }
 
 // defined in nms_frames_split.cu / nms_frames_big.cu (separate translation units: they compile in parallel)
-int launch_nms_frames_split(int nper, int npb, const NmsFramesParams& p, size_t smem, int grid, cudaStream_t st);
+int launch_nms_frames_split(int nper, int npb, int threads, const NmsFramesParams& p, size_t smem, int grid, cudaStream_t st);
 int launch_nms_frames_big(const NmsFramesParams& p, int grid, cudaStream_t st);
 size_t nms_frames_big_ws_bytes(int grid, int nb);
 

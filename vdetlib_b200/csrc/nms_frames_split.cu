@@ -6,14 +6,15 @@
 namespace vdet {
 
 template <int NPER, int NPB>
-static int launch_split(const NmsFramesParams& p, size_t smem, int grid, cudaStream_t st) {
+static int launch_split(int threads, const NmsFramesParams& p, size_t smem, int grid, cudaStream_t st) {
+    if (threads == NMS_THREADS_WIDE) return launch_nms_frames_t<NPER, NPB, true, NMS_THREADS_WIDE>(p, smem, grid, st);   // staged only
     return p.stage ? launch_nms_frames_t<NPER, NPB, true>(p, smem, grid, st)
                    : launch_nms_frames_t<NPER, NPB, false>(p, smem, grid, st);
 }
 
-int launch_nms_frames_split(int nper, int npb, const NmsFramesParams& p, size_t smem, int grid, cudaStream_t st) {
-    if (nper == 4 && npb == 1) return launch_split<4, 1>(p, smem, grid, st);
-    if (nper == 8 && npb == 2) return launch_split<8, 2>(p, smem, grid, st);
+int launch_nms_frames_split(int nper, int npb, int threads, const NmsFramesParams& p, size_t smem, int grid, cudaStream_t st) {
+    if (nper == 4 && npb == 1) return launch_split<4, 1>(threads, p, smem, grid, st);
+    if (nper == 8 && npb == 2) return launch_split<8, 2>(threads, p, smem, grid, st);
     set_error("nms_frames: no two-array variant for %d + %d keys per lane", nper, npb);
     return VDET_ERR_UNSUPPORTED;
 }
