@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Time vdet_nms_frames_f32 over a list of shapes under the library's measurement hooks (CUDA events, 4 rotating
 input sets).  usage: python tools/nms_shapes.py ["T,N,C" ...]
-Per shape: the default plan, VDET_NMS_THREADS=256 / 320 (CTA shape) and VDET_NMS_SPLIT_TAIL=1 (class-split last round)."""
+Per shape: the library's own plan, then VDET_NMS_THREADS=256 / 320 (the two CTA shapes); "same" = identical outputs."""
 import json
 import os
 import sys
@@ -16,8 +16,7 @@ shapes = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]] or [
     (1000, 300, 30), (1000, 300, 1), (1000, 300, 8), (1000, 300, 12), (1000, 150, 30), (1000, 64, 30), (1000, 256, 30),
     (40, 300, 30), (2000, 300, 30)]
 dev = torch.device("cuda", 0)
-hooks = [{}, {"VDET_NMS_THREADS": "256"}, {"VDET_NMS_THREADS": "320"}, {"VDET_NMS_SPLIT_TAIL": "1"},
-         {"VDET_NMS_THREADS": "256", "VDET_NMS_SPLIT_TAIL": "1"}]
+hooks = [{}, {"VDET_NMS_THREADS": "256"}, {"VDET_NMS_THREADS": "320"}]
 rows = []
 for T, N, C in shapes:
     sets = []
@@ -29,8 +28,7 @@ for T, N, C in shapes:
     ref = None
     rec = {"T": T, "N": N, "C": C}
     for h in hooks:
-        for k in ("VDET_NMS_THREADS", "VDET_NMS_SPLIT_TAIL"):
-            os.environ.pop(k, None)
+        os.environ.pop("VDET_NMS_THREADS", None)
         os.environ.update(h)
         out = None
         for k in range(3):

@@ -12,14 +12,10 @@ static void plan_items(NmsFramesParams& p, int slots) {
     // Only launches that cannot fill the grid once are split (a single image with 30 classes, a short
     // clip): measured on config 2, splitting the LAST round of a multi-round launch does not pay --
     // the CTAs of a thin last round already run alone on their SMs and finish early.
-    int rem = p.n_segs;
-    if (p.n_segs * 2 > slots) {
-        // measurement hook: cut the frames of a thin LAST round (at most half the slots) into class ranges
-        const char* e = getenv("VDET_NMS_SPLIT_TAIL");
-        if (!(e && atoi(e))) return;
-        rem = p.n_segs % slots;
-        if (rem == 0 || rem * 2 > slots) return;
-    }
+    // (again with the 10-warp shape: 1000 frames over 444 slots, the 112 frames of the third round cut in three:
+    // 0.288 ms against 0.278)
+    if (p.n_segs * 2 > slots) return;
+    const int rem = p.n_segs;
     int ns = slots / rem;
     if (ns > p.n_classes) ns = p.n_classes;
     if (ns > 8) ns = 8;
@@ -170,13 +166,22 @@ extern "C" int vdet_nms_frames_f32(const float* boxes, int box_ld,
         return q;
     };
     // CTA shape.  Default: 8 warps, up to 4 CTAs per SM, classes staged in up to 3 chunks.  Wide: 10 warps, 3 CTAs per
-    // SM -- taken when every class of the frame is staged at once at that residency (no chunk barriers) and there
-    // are enough classes to occupy the warps; frames of at most 320 boxes only (the kernels built for it).
+    // SM with every class of the frame staged at once (no chunk barriers); frames of at most 320 boxes only (the
+    // kernels built for it).  Measured (tools/nms_shapes.py, profiles/r02_nms_variants.md; 300 boxes, ms default / wide):
+    // 30 classes x 1000 frames 0.296 / 0.278, x 2000 frames 0.490 / 0.504, x 40 frames 0.055 / 0.057; 12 classes
+    // 0.173 / 0.183; 8 classes 0.133 / 0.141.  Hence: wide when its warps are dealt whole rounds of classes at least
+    // as well as the default's (rounds of classes per warp / CTAs per SM), and the launch is between half a round
+    // and two rounds of the default grid -- longer launches amortise the default's better steady state, shorter
+    // ones are split by class ranges anyway.
     int threads = NMS_THREADS;
     Plan plan = plan_for(NMS_THREADS / 32, (nper > 16) ? 1 : VDET_NMS_CTAS_PER_SM);
     if (nper <= 8 && want_stage) {
         const Plan wide = plan_for(NMS_THREADS_WIDE / 32, NMS_CTAS_WIDE);
-        bool take = wide.stage && wide.cls_chunk >= n_classes && wide.per_sm == NMS_CTAS_WIDE && n_classes >= NMS_THREADS_WIDE / 32;
+        const int ww = NMS_THREADS_WIDE / 32, wd = NMS_THREADS / 32;
+        const int slots_default = usable_sm_count() * VDET_NMS_CTAS_PER_SM;
+        bool take = wide.stage && wide.cls_chunk >= n_classes && wide.per_sm == NMS_CTAS_WIDE
+                    && VDET_NMS_CTAS_PER_SM * ((n_classes + ww - 1) / ww) <= NMS_CTAS_WIDE * ((n_classes + wd - 1) / wd)
+                    && 2 * n_segs > slots_default && n_segs <= 2 * slots_default;
         if (const char* e = getenv("VDET_NMS_THREADS")) {                 // measurement hook: 256 / 320
             const int t = atoi(e);
             if (t == NMS_THREADS) take = false;
