@@ -2,8 +2,13 @@
 // The kernel itself: nms_frames.cuh; two-array sort variants: nms_frames_split.cu; frames of 1025..2048 boxes:
 // nms_frames_big.cu.
 #include "nms_frames.cuh"
+#include "nms_plan.h"
 
 namespace vdet {
+
+static_assert(NMS_PLAN_WARPS_DEFAULT * 32 == NMS_THREADS && NMS_PLAN_CTAS_DEFAULT == VDET_NMS_CTAS_PER_SM &&
+              NMS_PLAN_WARPS_WIDE * 32 == NMS_THREADS_WIDE && NMS_PLAN_CTAS_WIDE == NMS_CTAS_WIDE,
+              "nms_plan.h models the CTA shapes of nms_frames.cuh");
 
 // Work items for a persistent grid of `slots` CTAs over n_segs frames (see NmsFramesParams).
 static void plan_items(NmsFramesParams& p, int slots) {
@@ -165,23 +170,14 @@ extern "C" int vdet_nms_frames_f32(const float* boxes, int box_ld,
         q.smem = base + (q.stage ? (size_t)(q.cls_chunk < n_classes ? q.cls_chunk : n_classes) * per_class : 0);
         return q;
     };
-    // CTA shape.  Default: 8 warps, up to 4 CTAs per SM, classes staged in up to 3 chunks.  Wide: 10 warps, 3 CTAs per
-    // SM with every class of the frame staged at once (no chunk barriers); frames of at most 320 boxes only (the
-    // kernels built for it).  Measured (tools/nms_shapes.py, profiles/r02_nms_variants.md; 300 boxes, ms default / wide):
-    // 30 classes x 1000 frames 0.296 / 0.278, x 2000 frames 0.490 / 0.504, x 40 frames 0.055 / 0.057; 12 classes
-    // 0.173 / 0.183; 8 classes 0.133 / 0.141.  Hence: wide when its warps are dealt whole rounds of classes at least
-    // as well as the default's (rounds of classes per warp / CTAs per SM), and the launch is between half a round
-    // and two rounds of the default grid -- longer launches amortise the default's better steady state, shorter
-    // ones are split by class ranges anyway.
+    // CTA shape (nms_plan.h): the default, or -- when it fits with every class staged at once and the launch
+    // quantises better on its 3-per-SM grid -- the wide one; frames of at most 320 boxes only (the kernels built).
     int threads = NMS_THREADS;
     Plan plan = plan_for(NMS_THREADS / 32, (nper > 16) ? 1 : VDET_NMS_CTAS_PER_SM);
     if (nper <= 8 && want_stage) {
         const Plan wide = plan_for(NMS_THREADS_WIDE / 32, NMS_CTAS_WIDE);
-        const int ww = NMS_THREADS_WIDE / 32, wd = NMS_THREADS / 32;
-        const int slots_default = usable_sm_count() * VDET_NMS_CTAS_PER_SM;
-        bool take = wide.stage && wide.cls_chunk >= n_classes && wide.per_sm == NMS_CTAS_WIDE
-                    && VDET_NMS_CTAS_PER_SM * ((n_classes + ww - 1) / ww) <= NMS_CTAS_WIDE * ((n_classes + wd - 1) / wd)
-                    && 2 * n_segs > slots_default && n_segs <= 2 * slots_default;
+        const bool fits = wide.stage && wide.cls_chunk >= n_classes && wide.per_sm == NMS_CTAS_WIDE;
+        bool take = fits && nms_prefer_wide(n_segs, n_classes, usable_sm_count());
         if (const char* e = getenv("VDET_NMS_THREADS")) {                 // measurement hook: 256 / 320
             const int t = atoi(e);
             if (t == NMS_THREADS) take = false;

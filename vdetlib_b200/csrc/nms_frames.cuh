@@ -88,7 +88,7 @@ __device__ __forceinline__ uint32_t unskew(const uint32_t words) { return words 
 
 // CTA shapes of the <= 1024-box variants: 8 warps, four CTAs per SM (64 registers per thread), or -- for frames of at
 // most 320 boxes whose classes are all staged at once -- 10 warps, three CTAs per SM: 30 classes are three per warp
-// with no chunk barrier in between (config 2: 0.294 -> 0.277 ms, profiles/r02_nms_variants.md).
+// with no chunk barrier in between (config 2: 0.294 -> 0.277 ms, profiles/r02_nms_variants.md); nms_plan.h picks.
 constexpr int NMS_THREADS = 256;
 constexpr int NMS_THREADS_WIDE = 320;
 constexpr int NMS_CTAS_WIDE = 3;
